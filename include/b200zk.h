@@ -1,0 +1,153 @@
+/*
+ * b200zk.h -- C ABI of libb200zk.so: the B200 (sm_100a) backend for the one data-parallel hot
+ * path under the Halo2/KZG prover and verifier of input-output-hk/plutus-halo2-verifier-gen:
+ * BLS12-381 G1 multi-scalar multiplication and the Fr NTT of the evaluation domain.
+ *
+ * The reference has no FFI of its own for this path: its arithmetic lives in the crates
+ * midnight-proofs =0.8.0 / midnight-curves =0.3.0 (-> blst), reached through the generic bound
+ *   PCS: ExtractPCS + PolynomialCommitmentScheme<Scalar, Commitment = G1Projective>
+ *   (/root/reference/src/plutus_gen/mod.rs:77,116,181; alias `type KZG = KZGCommitmentScheme<Bls12>`
+ *   at /root/reference/examples/simple_mul.rs:31).
+ * Each entry point below names the upstream function whose body it replaces and the
+ * reference call sites that reach it.  INTEGRATION.md shows the Rust `extern "C"` block and
+ * the PCS shim that binds them.
+ *
+ * Conventions
+ *   - every function returns int32_t: 0 = OK, negative = error class (B200ZK_ERR_*);
+ *     b200zk_last_error() returns the text of the calling thread's last failure.
+ *   - no exceptions cross the boundary; entry points may be called from any host thread
+ *     (calls are serialised on one device context per process: one process per GPU).
+ *   - there is NO CPU fallback: without a usable B200 every call fails with B200ZK_ERR_NO_DEVICE.
+ *
+ * Wire formats (little-endian throughout)
+ *   Fr  (midnight_curves::Fq, the 255-bit scalar field):
+ *        B200ZK_FMT_CANONICAL  32 bytes, integer; values >= r are reduced on read, as the proof
+ *                              wire format does (/root/reference/aiken-verifier/aiken_halo2/lib/transcript.ak:158-179)
+ *        B200ZK_FMT_MONT       32 bytes = 4 x u64 limbs of a*2^256 mod r: the in-memory form of
+ *                              blst_fr / midnight_curves::Fq, for a zero-copy Rust shim
+ *   G1 affine (midnight_curves::G1Affine): x || y, 48 bytes each
+ *        B200ZK_FMT_CANONICAL  integers < p;  B200ZK_FMT_MONT  6 x u64 limbs of a*2^384 mod p
+ *                              (blst_p1_affine)
+ *        the identity is (0, 0) in both (/root/reference/plinth-verifier/plutus-halo2/src/Plutus/Crypto/Halo2/CompressUncompress.hs:72)
+ *   compressed G1: 48 bytes big-endian x with flag bits 0x80 compressed / 0x40 infinity /
+ *        0x20 y-is-larger (/root/reference/aiken-verifier/aiken_halo2/lib/bls_utils.ak:17-49)
+ *   "_dev" entry points take device pointers (16-byte aligned) and a cudaStream_t passed as void*.
+ */
+#ifndef B200ZK_H
+#define B200ZK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ZK_OK 0
+#define B200ZK_ERR_INVALID_ARG (-1)
+#define B200ZK_ERR_CUDA (-2)
+#define B200ZK_ERR_NO_DEVICE (-3)
+#define B200ZK_ERR_BAD_HANDLE (-4)
+#define B200ZK_ERR_OOM (-5)
+#define B200ZK_ERR_NOT_INIT (-6)
+#define B200ZK_ERR_BAD_POINT (-7) /* a base is not a canonical point of the curve */
+
+#define B200ZK_FMT_CANONICAL 0u
+#define B200ZK_FMT_MONT 1u
+
+/* NTT flags */
+#define B200ZK_NTT_INVERSE_SCALE 1u /* multiply the result by 1/n (caller passes omega^-1) */
+#define B200ZK_NTT_COSET_IN 2u      /* x[i] *= shift^i before the transform  (coeff_to_extended) */
+#define B200ZK_NTT_COSET_OUT 4u     /* y[i] *= shift^i after the transform   (extended_to_coeff, shift = g^-1) */
+#define B200ZK_NTT_MONT 8u          /* data is in Montgomery form (in and out); omega/shift stay canonical */
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+/* Binds the process to one GPU (one process per GPU).  device < 0 selects the current device. */
+int32_t b200zk_init(int32_t device);
+int32_t b200zk_shutdown(void);
+int32_t b200zk_last_error(char *buf, size_t len);
+/* name, SM count and compute capability of the bound device, e.g. "NVIDIA B200 sm_100 148SM" */
+int32_t b200zk_device_info(char *buf, size_t len);
+/* pinned host memory, so that the host<->device copies inside the entry points run at link speed */
+int32_t b200zk_host_alloc(void **out, size_t bytes);
+int32_t b200zk_host_free(void *p);
+
+/* ---- base tables ------------------------------------------------------------------------
+ * Replaces nothing; this is the device residency of ParamsKZG::{g, g_lagrange}
+ * (/root/reference/src/kzg_params.rs:33-80): upload once, commit many times.
+ * stride_bytes = distance between consecutive points in the source (>= 96, multiple of 4; 0 = 96),
+ * which lets a shim pass a slice of a wider Rust struct without repacking.               */
+int32_t b200zk_bases_register(const uint8_t *g1_affine, uint64_t n, uint32_t fmt, uint32_t stride_bytes,
+                              uint64_t *out_handle);
+int32_t b200zk_bases_register_dev(const void *d_g1_affine, uint64_t n, uint32_t fmt, uint32_t stride_bytes,
+                                  uint64_t *out_handle);
+int32_t b200zk_bases_release(uint64_t handle);
+/* copies points [start, start+n) of a table back to the host in canonical wire format */
+int32_t b200zk_bases_read(uint64_t handle, uint64_t start, uint64_t n, uint8_t *out_affine);
+
+/* ---- G1 MSM -----------------------------------------------------------------------------
+ * Replaces midnight_curves G1Projective::multi_exp / blst p1s_mult_pippenger under
+ *   KZGCommitmentScheme::commit_lagrange  (advice, lookup, permutation, instance columns:
+ *       /root/reference/examples/simple_mul.rs:62,72; /root/reference/src/circuits/atms_circuit.rs:247,296;
+ *       /root/reference/examples/schnorr.rs:115)
+ *   KZGCommitmentScheme::commit           (h pieces, random poly, f and pi of multi_open:
+ *       order pinned by /root/reference/src/plutus_gen/extraction/pcs/kzg.rs:55-79)
+ * result = sum_{i<n} scalars[i] * bases[offset + i], affine canonical wire format (96 bytes).  */
+int32_t b200zk_msm_g1(uint64_t bases, uint64_t offset, const uint8_t *scalars, uint64_t n, uint32_t scalar_fmt,
+                      uint8_t out_affine[96]);
+/* `batch` scalar vectors of the same length n against one table: the prover's pattern
+ * (one MSM per committed column); scalars = batch*n elements, out = batch*96 bytes.          */
+int32_t b200zk_msm_g1_batch(uint64_t bases, uint64_t offset, const uint8_t *scalars, uint64_t n, uint32_t batch,
+                            uint32_t scalar_fmt, uint8_t *out_affine);
+/* Bases that are not resident: the verifier's DualMSM left/right sums
+ * (Guard::verify / DualMSM::check, /root/reference/examples/simple_mul.rs:98-102,
+ * /root/reference/examples/ivc.rs:196; batch_verify, /root/reference/src/circuits/schnorr_circuit.rs:224).     */
+int32_t b200zk_msm_g1_adhoc(const uint8_t *g1_affine, uint32_t point_fmt, const uint8_t *scalars, uint32_t scalar_fmt,
+                            uint64_t n, uint8_t out_affine[96]);
+/* Device-resident variant: scalars already in HBM, result (Montgomery affine, 96 bytes) written
+ * to d_out_mont and/or (canonical) to d_out_canon; asynchronous on `stream`.                  */
+int32_t b200zk_msm_g1_dev(uint64_t bases, uint64_t offset, const void *d_scalars, uint64_t n, uint32_t batch,
+                          uint32_t scalar_fmt, void *d_out_mont, void *d_out_canon, void *stream);
+/* Sum of n affine points: combines the per-GPU partial results of a point-range sharded MSM
+ * (Montgomery affine in HBM, e.g. the all-gathered d_out_mont of every rank).                */
+int32_t b200zk_g1_sum_dev(const void *d_points_mont, uint32_t n, void *d_out_mont, void *d_out_canon, void *stream);
+
+/* ---- Fr NTT -----------------------------------------------------------------------------
+ * Replaces midnight_proofs best_fft / EvaluationDomain::{lagrange_to_coeff, coeff_to_lagrange,
+ * coeff_to_extended, extended_to_coeff} (constructed inside keygen/create_proof; explicit at
+ * /root/reference/examples/ivc.rs:109, /root/reference/src/circuits/ivc_circuit.rs:305).
+ * X[k] = sum_i x[i] omega^(ik), natural order in and out, in place; n = 2^log_n.
+ * omega and coset_shift are canonical 32-byte Fr; coset_shift may be NULL without COSET flags. */
+int32_t b200zk_ntt_fr(uint8_t *data, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
+                      const uint8_t coset_shift[32]);
+/* `batch` polynomials stored back to back (batch * 2^log_n elements) */
+int32_t b200zk_ntt_fr_batch(uint8_t *data, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
+                            const uint8_t coset_shift[32]);
+int32_t b200zk_ntt_fr_dev(void *d_data, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
+                          const uint8_t coset_shift[32], void *stream);
+
+/* ---- encodings --------------------------------------------------------------------------
+ * ZCash compressed form of an affine canonical point: what the transcript absorbs and the proof
+ * carries (/root/reference/aiken-verifier/aiken_halo2/lib/transcript.ak:62-83,121-156).  Host-side byte logic. */
+int32_t b200zk_g1_compress(const uint8_t affine[96], uint8_t out[48]);
+
+/* ---- synthetic inputs and self-test (bench / tests) ------------------------------------------
+ * bases P_i = a_i*G with a_i = splitmix64(seed + start + i), written as packed Montgomery affine. */
+int32_t b200zk_g1_synth_bases_dev(uint64_t seed, uint64_t start, uint64_t n, void *d_out_mont, void *stream);
+/* elementwise field ops on device arrays, for limb-for-limb parity tests of the arithmetic layer:
+ * op 0 mul, 1 add, 2 sub, 3 inverse(a); field 0 = Fr (32 B), 1 = Fp (48 B); canonical in/out.    */
+int32_t b200zk_selftest_field(uint32_t field, uint32_t op, const uint8_t *a, const uint8_t *b, uint8_t *out,
+                              uint64_t count);
+/* integer-pipe micro-benchmark: kind 0 = IMAD.WIDE.U32 chains, 1 = IMAD lo+hi pairs, 2 = Fp Montgomery
+ * multiplications, 3 = XYZZ mixed additions, 4 = Fr multiplications.  *out_ops_per_s receives
+ * limb-MACs (kinds 0,1), multiplications (2,4) or additions (3) per second over all SMs.           */
+int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double *out_ops_per_s, double *out_ms);
+/* number of kernels this library has launched since init (bench.py's gpu_launches counter) */
+uint64_t b200zk_launch_count(void);
+/* overrides for experiments: MSM window bits (0 = automatic) and max entries per task (0 = automatic) */
+int32_t b200zk_set_msm_tuning(uint32_t window_bits, uint32_t smax);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ZK_H */

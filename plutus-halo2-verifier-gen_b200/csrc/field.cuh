@@ -1,0 +1,305 @@
+// field.cuh -- Montgomery arithmetic for the two BLS12-381 fields on 32-bit limbs,
+// written for the sm_100a integer pipe (IMAD.WIDE with carry).
+//
+//   Fp : 381-bit base field,   12 x u32, R = 2^384  (replaces blst fp, reached through
+//        midnight_curves::Fp -- /root/reference/Cargo.toml:27, used at
+//        /root/reference/src/plutus_gen/proof_serialization.rs:43,58-59)
+//   Fr : 255-bit scalar field,  8 x u32, R = 2^256  (midnight_curves::Fq, the type of every
+//        polynomial coefficient -- /root/reference/examples/simple_mul.rs:7)
+//
+// The limb layout of a Montgomery-form element is byte-identical to blst's 6x/4x u64
+// little-endian limbs, so the "MONT" wire formats of include/b200zk.h are zero-copy.
+//
+// Multiplication uses the even/odd column split: the products a[j]*b_i for even j land on
+// 64-bit pairs (0,1),(2,3).. of one accumulator and for odd j on the pairs of a second
+// accumulator that is aligned one limb higher, so every row is a run of IMAD.WIDE.U32
+// with the carry riding on a predicate, and the division by 2^32 of each Montgomery step
+// is a swap of the two accumulators instead of a register shuffle.
+//
+// Every function is __host__ __device__: on the host the carry flag is emulated, which
+// lets tests/host_kernels_test.cu run the very same algorithm against the oracle on a box without
+// a GPU.  The product never runs the host path.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HD __host__ __device__ __forceinline__
+#else
+#define HD inline
+#endif
+
+namespace b200zk {
+
+// ---------------------------------------------------------------------------------------
+// carry-chain primitives
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+#define B200ZK_CC_DECL
+HD uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+HD uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+HD uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+HD uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+HD uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+HD uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// (hi:lo) = a*b + (chi:clo), carry-out to CC.  ptxas fuses each lo/hi pair into one IMAD.WIDE.U32.
+HD void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+    asm volatile("mad.lo.cc.u32 %0, %2, %3, %4;\n\tmadc.hi.cc.u32 %1, %2, %3, %5;"
+                 : "=r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
+}
+// same with carry-in from CC
+HD void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %4;\n\tmadc.hi.cc.u32 %1, %2, %3, %5;"
+                 : "=r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
+}
+HD void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+#else
+// host emulation of the PTX carry flag (tests only)
+static thread_local uint32_t t_cc = 0;
+HD uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; t_cc = (uint32_t)(s >> 32); return (uint32_t)s; }
+HD uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b + t_cc; t_cc = (uint32_t)(s >> 32); return (uint32_t)s; }
+HD uint32_t addc(uint32_t a, uint32_t b) { return a + b + t_cc; }
+HD uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b; t_cc = (uint32_t)(s >> 32) & 1; return (uint32_t)s; }
+HD uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b - t_cc; t_cc = (uint32_t)(s >> 32) & 1; return (uint32_t)s; }
+HD uint32_t subc(uint32_t a, uint32_t b) { return a - b - t_cc; }
+HD void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+    uint64_t pr = (uint64_t)a * b;
+    uint64_t l = (pr & 0xffffffffu) + clo;
+    uint64_t h = (pr >> 32) + chi + (l >> 32);
+    lo = (uint32_t)l; hi = (uint32_t)h; t_cc = (uint32_t)(h >> 32);
+}
+HD void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+    uint64_t pr = (uint64_t)a * b;
+    uint64_t l = (pr & 0xffffffffu) + clo + t_cc;
+    uint64_t h = (pr >> 32) + chi + (l >> 32);
+    lo = (uint32_t)l; hi = (uint32_t)h; t_cc = (uint32_t)(h >> 32);
+}
+HD void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    uint64_t pr = (uint64_t)a * b; lo = (uint32_t)pr; hi = (uint32_t)(pr >> 32);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------
+// field parameters
+// ---------------------------------------------------------------------------------------
+#define B200ZK_FP_P   {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, \
+                       0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau}
+#define B200ZK_FP_PM2 {0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, \
+                       0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau}
+#define B200ZK_FP_R   {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u, \
+                       0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u}
+#define B200ZK_FP_R2  {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu, \
+                       0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u}
+#define B200ZK_FR_P   {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u}
+#define B200ZK_FR_PM2 {0xffffffffu, 0xfffffffeu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u}
+#define B200ZK_FR_R   {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u}
+#define B200ZK_FR_R2  {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u}
+
+// BLS12-381 base-field modulus p (BlsTypes.hs:102-103 / bls_utils.ak:14-15) and scalar-field
+// modulus r (BlsTypes.hs:97), with R mod m, R^2 mod m and m-2.  Device code reads the
+// __constant__ copies (they fold into IMAD operands as c[bank][off]); the host copies exist
+// only for the CPU-side algorithm tests.
+#if defined(__CUDACC__)
+__device__ __constant__ uint32_t c_fp_p[12] = B200ZK_FP_P, c_fp_pm2[12] = B200ZK_FP_PM2, c_fp_r[12] = B200ZK_FP_R, c_fp_r2[12] = B200ZK_FP_R2;
+__device__ __constant__ uint32_t c_fr_p[8] = B200ZK_FR_P, c_fr_pm2[8] = B200ZK_FR_PM2, c_fr_r[8] = B200ZK_FR_R, c_fr_r2[8] = B200ZK_FR_R2;
+#endif
+static const uint32_t h_fp_p[12] = B200ZK_FP_P, h_fp_pm2[12] = B200ZK_FP_PM2, h_fp_r[12] = B200ZK_FP_R, h_fp_r2[12] = B200ZK_FP_R2;
+static const uint32_t h_fr_p[8] = B200ZK_FR_P, h_fr_pm2[8] = B200ZK_FR_PM2, h_fr_r[8] = B200ZK_FR_R, h_fr_r2[8] = B200ZK_FR_R2;
+
+#ifdef __CUDA_ARCH__
+#define B200ZK_SEL(name) c_##name
+#else
+#define B200ZK_SEL(name) h_##name
+#endif
+
+struct FpParams {
+    static constexpr int N = 12;
+    static constexpr uint32_t M0 = 0xfffcfffdu;  // -p^-1 mod 2^32
+    HD static uint32_t p(int i) { return B200ZK_SEL(fp_p)[i]; }
+    HD static uint32_t pm2(int i) { return B200ZK_SEL(fp_pm2)[i]; }
+    HD static uint32_t r(int i) { return B200ZK_SEL(fp_r)[i]; }
+    HD static uint32_t r2(int i) { return B200ZK_SEL(fp_r2)[i]; }
+};
+struct FrParams {
+    static constexpr int N = 8;
+    static constexpr uint32_t M0 = 0xffffffffu;
+    HD static uint32_t p(int i) { return B200ZK_SEL(fr_p)[i]; }
+    HD static uint32_t pm2(int i) { return B200ZK_SEL(fr_pm2)[i]; }
+    HD static uint32_t r(int i) { return B200ZK_SEL(fr_r)[i]; }
+    HD static uint32_t r2(int i) { return B200ZK_SEL(fr_r2)[i]; }
+};
+
+// ---------------------------------------------------------------------------------------
+// Field element: fully reduced, Montgomery form
+// ---------------------------------------------------------------------------------------
+template <class P>
+struct Fe {
+    static constexpr int N = P::N;
+    uint32_t l[N];
+};
+
+template <class P> HD Fe<P> fe_zero() { Fe<P> r; for (int i = 0; i < P::N; i++) r.l[i] = 0; return r; }
+template <class P> HD Fe<P> fe_one() { Fe<P> r; for (int i = 0; i < P::N; i++) r.l[i] = P::r(i); return r; }
+template <class P> HD bool fe_is_zero(const Fe<P>& a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) o |= a.l[i];
+    return o == 0;
+}
+template <class P> HD bool fe_eq(const Fe<P>& a, const Fe<P>& b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) o |= a.l[i] ^ b.l[i];
+    return o == 0;
+}
+
+// r = a - p if a >= p else a   (a < 2p)
+template <class P> HD void fe_cond_sub_p(Fe<P>& a) {
+    constexpr int N = P::N;
+    uint32_t t[N];
+    t[0] = sub_cc(a.l[0], P::p(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = subc_cc(a.l[i], P::p(i));
+    uint32_t borrow = subc(0, 0);  // 0xffffffff if a < p
+#pragma unroll
+    for (int i = 0; i < N; i++) a.l[i] = borrow ? a.l[i] : t[i];
+}
+
+template <class P> HD Fe<P> fe_add(const Fe<P>& a, const Fe<P>& b) {
+    constexpr int N = P::N;
+    Fe<P> r;
+    r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+    // both moduli leave the top bit of the top limb clear, so a+b < 2p never carries out
+    fe_cond_sub_p(r);
+    return r;
+}
+template <class P> HD Fe<P> fe_sub(const Fe<P>& a, const Fe<P>& b) {
+    constexpr int N = P::N;
+    Fe<P> r;
+    r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+    uint32_t mask = subc(0, 0);  // all ones on borrow
+    r.l[0] = add_cc(r.l[0], P::p(0) & mask);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(r.l[i], P::p(i) & mask);
+    r.l[N - 1] = addc(r.l[N - 1], P::p(N - 1) & mask);
+    return r;
+}
+template <class P> HD Fe<P> fe_neg(const Fe<P>& a) { return fe_sub(fe_zero<P>(), a); }
+template <class P> HD Fe<P> fe_dbl(const Fe<P>& a) { return fe_add(a, a); }
+
+// One Montgomery step on the (E, O) accumulator pair: E += a_even*bi, O' = (old E >> 64) + a_odd*bi,
+// then add m*p so that E[0] becomes 0.  On entry E is the accumulator that was "odd" in the
+// previous step and O the one that was "even" (its limb 0 is already zero, limb 1 still pending).
+template <class P> HD void mont_step(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi) {
+    constexpr int N = P::N;
+    E[0] = add_cc(E[0], O[1]);
+#pragma unroll
+    for (int k = 0; k < N - 2; k += 2) madc_wide_cc(O[k], O[k + 1], a[k + 1], bi, O[k + 2], O[k + 3]);
+    madc_wide_cc(O[N - 2], O[N - 1], a[N - 1], bi, 0, 0);
+    mad_wide_cc(E[0], E[1], a[0], bi, E[0], E[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], a[j], bi, E[j], E[j + 1]);
+    O[N - 1] = addc(O[N - 1], 0);
+    uint32_t m = E[0] * P::M0;
+    mad_wide_cc(O[0], O[1], P::p(1), m, O[0], O[1]);
+#pragma unroll
+    for (int k = 2; k < N; k += 2) madc_wide_cc(O[k], O[k + 1], P::p(k + 1), m, O[k], O[k + 1]);
+    mad_wide_cc(E[0], E[1], P::p(0), m, E[0], E[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], P::p(j), m, E[j], E[j + 1]);
+    O[N - 1] = addc(O[N - 1], 0);
+}
+
+// r = a*b/R mod p, inputs and output fully reduced
+template <class P> HD Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+    constexpr int N = P::N;
+    uint32_t ev[N], od[N];
+    // step 0: plain products, then the m*p row
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+        mul_wide(ev[j], ev[j + 1], a.l[j], b.l[0]);
+        mul_wide(od[j], od[j + 1], a.l[j + 1], b.l[0]);
+    }
+    {
+        uint32_t m = ev[0] * P::M0;
+        mad_wide_cc(od[0], od[1], P::p(1), m, od[0], od[1]);
+#pragma unroll
+        for (int k = 2; k < N; k += 2) madc_wide_cc(od[k], od[k + 1], P::p(k + 1), m, od[k], od[k + 1]);
+        mad_wide_cc(ev[0], ev[1], P::p(0), m, ev[0], ev[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) madc_wide_cc(ev[j], ev[j + 1], P::p(j), m, ev[j], ev[j + 1]);
+        od[N - 1] = addc(od[N - 1], 0);
+    }
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+        mont_step<P>(od, ev, a.l, b.l[i]);
+        if (i + 1 < N) mont_step<P>(ev, od, a.l, b.l[i + 1]);
+    }
+    // N is even: the last step ran with E = od, O = ev, so the value is ev + (od >> 32)
+    Fe<P> r;
+    r.l[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(ev[i], od[i + 1]);
+    r.l[N - 1] = addc(ev[N - 1], 0);
+    fe_cond_sub_p(r);
+    return r;
+}
+template <class P> HD Fe<P> fe_sqr(const Fe<P>& a) { return fe_mul(a, a); }
+
+// canonical (non-Montgomery) limbs -> Montgomery form, and back
+template <class P> HD Fe<P> fe_to_mont(const Fe<P>& a) {
+    Fe<P> r2;
+    for (int i = 0; i < P::N; i++) r2.l[i] = P::r2(i);
+    return fe_mul(a, r2);
+}
+template <class P> HD Fe<P> fe_from_mont(const Fe<P>& a) {
+    Fe<P> one = fe_zero<P>();
+    one.l[0] = 1;
+    return fe_mul(a, one);
+}
+// reduce an arbitrary N-limb value (< 2^(32N)) below p by repeated subtraction (Fr: < 3r; Fp wire
+// values are required to be canonical already, the loop then runs zero times)
+template <class P> HD void fe_reduce_loose(Fe<P>& a) {
+    constexpr int N = P::N;
+    for (int it = 0; it < 8; it++) {
+        uint32_t t[N];
+        t[0] = sub_cc(a.l[0], P::p(0));
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = subc_cc(a.l[i], P::p(i));
+        uint32_t borrow = subc(0, 0);
+        if (borrow) break;
+#pragma unroll
+        for (int i = 0; i < N; i++) a.l[i] = t[i];
+    }
+}
+
+// a^(p-2) by square-and-multiply over the bits of p-2 (constant exponent)
+template <class P> HD Fe<P> fe_inv(const Fe<P>& a) {
+    constexpr int N = P::N;
+    Fe<P> acc = fe_one<P>();
+    for (int i = N * 32 - 1; i >= 0; i--) {
+        acc = fe_sqr(acc);
+        if ((P::pm2(i >> 5) >> (i & 31)) & 1) acc = fe_mul(acc, a);
+    }
+    return acc;
+}
+// a^e for a small runtime exponent
+template <class P> HD Fe<P> fe_pow_u64(const Fe<P>& a, uint64_t e) {
+    Fe<P> acc = fe_one<P>(), base = a;
+    while (e) {
+        if (e & 1) acc = fe_mul(acc, base);
+        base = fe_sqr(base);
+        e >>= 1;
+    }
+    return acc;
+}
+
+typedef Fe<FpParams> Fp;
+typedef Fe<FrParams> Fr;
+
+}  // namespace b200zk

@@ -1,0 +1,224 @@
+// ntt.cuh -- Fr number-theoretic transform for sm_100a.
+//
+// Replaces the butterflies behind midnight_proofs::poly::EvaluationDomain
+// {lagrange_to_coeff, coeff_to_extended, extended_to_coeff, coeff_to_lagrange} / best_fft
+// (constructed inside keygen/create_proof; explicit call sites
+// /root/reference/examples/ivc.rs:109, /root/reference/src/circuits/ivc_circuit.rs:305).
+// Convention (pinned by /root/reference/aiken-verifier/aiken_halo2/lib/omega_rotations.ak:48-81):
+// X[k] = sum_i x[i] * omega^(i*k), natural order in and out; the caller passes omega.
+//
+// Structure: a Stockham autosort decomposition into 1..3 passes of radix R = 2^deg (deg <= 11).
+// In a pass with current length m and stride s (s*m = n), the R-point sub-transform number
+// u = q + s*p reads x[u + j*n/R] (j < R) and writes y[q + s*(R*p + k)] * omega_m^(p*k).
+// One CTA stages 2048 elements (= 2048/R sub-transforms with consecutive u, so global reads are
+// contiguous across u) in shared memory as 8 word-planes and runs the R-point transform as
+// in-place decimation-in-frequency, three radix-2 stages at a time in registers (8 elements
+// per thread); the bit reversal of DIF is undone in the address of the final store.
+// Per-pass twiddles omega_m^(p*k), the 1/n of an inverse transform and the coset powers are
+// table look-ups laid out exactly like the data they multiply.
+#pragma once
+#include "field.cuh"
+
+namespace b200zk {
+
+constexpr int NTT_LOGB = 11;                  // log2(elements per CTA)
+constexpr int NTT_B = 1 << NTT_LOGB;          // 2048 elements = 64 KiB of Fr
+constexpr int NTT_THREADS = NTT_B / 8;        // 8 elements per thread
+constexpr int NTT_PLANE = NTT_B + NTT_B / 32; // one pad word per 32 elements
+constexpr size_t NTT_SMEM = (size_t)8 * NTT_PLANE * sizeof(uint32_t);
+
+struct NttPassArgs {
+    const uint32_t* in;       // Fr elements as 8 x u32
+    uint32_t* out;
+    const uint32_t* tw_local; // omega_R^e, e < R/2 (Montgomery form)
+    const uint32_t* tw_pass;  // T[p*R + k] = omega_m^(p*k) (x 1/n where folded) or nullptr
+    const uint32_t* in_scale; // per-element multiplier indexed like the input, or nullptr
+    const uint32_t* out_scale;// per-element multiplier indexed like the output, or nullptr
+    uint32_t log_n;
+    uint32_t deg;             // log2 R
+    uint32_t log_s;           // log2 of the stride s
+    uint32_t log_cols;        // log2(n / R): sub-transforms per polynomial
+    uint64_t total_cols;      // batch * n / R
+    const uint32_t* scalar;   // multiply every output by *scalar (1/n of a single-pass inverse), or nullptr
+    uint32_t reduce_in;       // canonical input may be >= r: reduce on read (transcript.ak:158-179)
+};
+
+__device__ __forceinline__ uint32_t ntt_pad(uint32_t e) { return e + (e >> 5); }
+
+__device__ __forceinline__ Fr ntt_lds(const uint32_t* sm, uint32_t e) {
+    Fr r;
+    uint32_t pos = ntt_pad(e);
+#pragma unroll
+    for (int w = 0; w < 8; w++) r.l[w] = sm[w * NTT_PLANE + pos];
+    return r;
+}
+__device__ __forceinline__ void ntt_sts(uint32_t* sm, uint32_t e, const Fr& v) {
+    uint32_t pos = ntt_pad(e);
+#pragma unroll
+    for (int w = 0; w < 8; w++) sm[w * NTT_PLANE + pos] = v.l[w];
+}
+__device__ __forceinline__ Fr ntt_ldg(const uint32_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ Fr ntt_ld(const uint32_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void ntt_st(uint32_t* p, const Fr& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+// radix-2 DIF stages on index bits lb+NB-1 .. lb of the CTA-local array; the thread owns the 8
+// elements whose index differs in bits lb..lb+2.
+template <int NB>
+__device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restrict__ tw_local, uint32_t deg,
+                                          uint32_t lb, uint32_t tid) {
+    // lanes walk the low index bits when that is conflict-free (lb >= 5), else the high bits
+    uint32_t lo, hi;
+    if (lb >= 5) {
+        lo = tid & ((1u << lb) - 1);
+        hi = tid >> lb;
+    } else {
+        hi = tid & ((1u << (NTT_LOGB - 3 - lb)) - 1);
+        lo = tid >> (NTT_LOGB - 3 - lb);
+    }
+    uint32_t base = (hi << (lb + 3)) | lo;
+    Fr v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = ntt_lds(sm, base | ((uint32_t)j << lb));
+    uint32_t rmask = (1u << deg) - 1;
+#pragma unroll
+    for (int q = NB - 1; q >= 0; q--) {
+        uint32_t b = lb + q;                       // index bit of this stage
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (j & (1 << q)) continue;
+            Fr x = v[j], y = v[j | (1 << q)];
+            v[j] = fe_add(x, y);
+            Fr d = fe_sub(x, y);
+            if (q == 0 && lb == 0) {               // twiddle exponent is 0 on the last stage
+                v[j | (1 << q)] = d;
+            } else {
+                uint32_t il = (base | ((uint32_t)j << lb)) & rmask;
+                uint32_t e = (il & ((1u << b) - 1)) << (deg - 1 - b);
+                v[j | (1 << q)] = fe_mul(d, ntt_ldg(tw_local + 8 * (size_t)e));
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) ntt_sts(sm, base | ((uint32_t)j << lb), v[j]);
+}
+
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) {
+    extern __shared__ uint32_t sm[];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t deg = a.deg;
+    const uint32_t logU = NTT_LOGB - deg;          // sub-transforms per CTA (log2)
+    const uint64_t col0 = (uint64_t)blockIdx.x << logU;
+    const uint64_t cmask = ((uint64_t)1 << a.log_cols) - 1;
+
+    // ---- load: element (ul, j) <- x[poly*n + u + j*(n/R)], ul fastest so consecutive lanes read
+    //      consecutive u
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        uint32_t idx = tid + t * NTT_THREADS;
+        uint32_t ul = idx & ((1u << logU) - 1), j = idx >> logU;
+        uint64_t col = col0 + ul;
+        Fr v = fe_zero<FrParams>();
+        if (col < a.total_cols) {
+            uint64_t poly = col >> a.log_cols, u = col & cmask;
+            uint64_t gi = (poly << a.log_n) + u + ((uint64_t)j << a.log_cols);
+            v = ntt_ld(a.in + 8 * gi);
+            if (a.reduce_in) fe_reduce_loose(v);
+            if (a.in_scale) v = fe_mul(v, ntt_ldg(a.in_scale + 8 * (u + ((uint64_t)j << a.log_cols))));
+        }
+        ntt_sts(sm, (ul << deg) | j, v);
+    }
+    __syncthreads();
+
+    // ---- R-point DIF transforms, three index bits per sweep
+    int rem = (int)deg;
+    while (rem > 0) {
+        int nb = rem >= 3 ? 3 : rem;
+        uint32_t lb = (uint32_t)(rem - nb);
+        if (nb == 3) ntt_group<3>(sm, a.tw_local, deg, lb, tid);
+        else if (nb == 2) ntt_group<2>(sm, a.tw_local, deg, lb, tid);
+        else ntt_group<1>(sm, a.tw_local, deg, lb, tid);
+        __syncthreads();
+        rem -= nb;
+    }
+
+    // ---- store: y[poly*n + q + s*(R*p + k)] = X_u[k] * T[p*R + k]; X_u[k] sits at bitrev(k).
+    //      First pass (s = 1): k fastest.  Later passes: ul (-> q) fastest.
+    const bool k_fast = (a.log_s == 0);
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        uint32_t idx = tid + t * NTT_THREADS;
+        uint32_t ul, k;
+        if (k_fast) { k = idx & ((1u << deg) - 1); ul = idx >> deg; }
+        else { ul = idx & ((1u << logU) - 1); k = idx >> logU; }
+        uint64_t col = col0 + ul;
+        if (col >= a.total_cols) continue;
+        uint32_t kr = __brev(k) >> (32 - deg);
+        if (deg == 0) kr = 0;
+        Fr v = ntt_lds(sm, (ul << deg) | kr);
+        uint64_t poly = col >> a.log_cols, u = col & cmask;
+        uint64_t q = u & (((uint64_t)1 << a.log_s) - 1), p = u >> a.log_s;
+        if (a.tw_pass) v = fe_mul(v, ntt_ldg(a.tw_pass + 8 * ((p << deg) + k)));
+        uint64_t oi = q + (((p << deg) + k) << a.log_s);
+        if (a.out_scale) v = fe_mul(v, ntt_ldg(a.out_scale + 8 * oi));
+        if (a.scalar) v = fe_mul(v, ntt_ldg(a.scalar));
+        ntt_st(a.out + 8 * ((poly << a.log_n) + oi), v);
+    }
+}
+
+// out[i] = scale * base^(e0 + i*mult mod 2^64), generic table generator (Montgomery form in and out).
+// kind 0: exponent = i * mult.  kind 1 (pass table): i = p*R + k, exponent = mult * p * k.
+__global__ void fr_powers_kernel(uint32_t* out, const uint32_t* base_p, const uint32_t* scale_p, uint64_t count,
+                                 uint64_t mult, uint32_t kind, uint32_t deg) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Fr base = ntt_ld(base_p);
+    uint64_t e;
+    if (kind == 0) e = i * mult;
+    else {
+        uint64_t p = i >> deg, k = i & (((uint64_t)1 << deg) - 1);
+        e = mult * p * k;
+    }
+    Fr acc = scale_p ? ntt_ld(scale_p) : fe_one<FrParams>();
+    while (e) {
+        if (e & 1) acc = fe_mul(acc, base);
+        base = fe_sqr(base);
+        e >>= 1;
+    }
+    ntt_st(out + 8 * i, acc);
+}
+
+// out = (Montgomery form of) 1 / 2^log_n ; single thread
+__global__ void fr_inv_pow2_kernel(uint32_t* out, uint32_t log_n) {
+    Fr two = fe_dbl(fe_one<FrParams>());
+    Fr n = fe_pow_u64(two, log_n);
+    ntt_st(out, fe_inv(n));
+}
+// elementwise conversions between canonical and Montgomery form (wire-format helpers)
+__global__ void fr_convert_kernel(uint32_t* data, uint64_t count, uint32_t to_mont) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Fr v = ntt_ld(data + 8 * i);
+    if (to_mont) { fe_reduce_loose(v); v = fe_to_mont(v); }
+    else v = fe_from_mont(v);
+    ntt_st(data + 8 * i, v);
+}
+
+}  // namespace b200zk

@@ -1,0 +1,239 @@
+"""Host-side mirror of the reference-facing interface for the MSM / NTT path.
+
+The reference reaches this path only through upstream traits (the crate sources are not in
+/root/reference, so the trait shapes below are restated from the reference's call sites):
+
+* ``ParamsKZG``                       /root/reference/src/kzg_params.rs:33-80 (SRS cache; the MSM bases)
+* ``KZGCommitmentScheme::commit`` /
+  ``commit_lagrange``                 reached via create_proof / keygen_vk,
+                                      /root/reference/examples/simple_mul.rs:62,72
+* ``EvaluationDomain``                /root/reference/examples/ivc.rs:109,
+                                      /root/reference/src/circuits/ivc_circuit.rs:305
+* ``DualMSM`` (``Guard::verify``)     /root/reference/examples/simple_mul.rs:98-102, examples/ivc.rs:196;
+                                      the two sums are spelled out at
+                                      /root/reference/aiken-verifier/aiken_halo2/lib/halo2_kzg.ak:15-44
+
+Everything numeric is done by libb200zk.so on the GPU; this file only marshals buffers and
+computes domain constants (a handful of modular exponentiations with Python ints).
+Polynomials are byte strings of 32-byte little-endian canonical Fr elements; points are
+96-byte affine wire-format strings (see include/b200zk.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+from . import capi
+from .capi import FMT_CANONICAL, NTT_COSET_IN, NTT_COSET_OUT, NTT_INVERSE_SCALE, addr, check, lib
+
+# scalar field of BLS12-381 (plinth-verifier/plutus-halo2/src/Plutus/Crypto/BlsTypes.hs:97)
+R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+TWO_ADICITY = 32
+MULTIPLICATIVE_GENERATOR = 7  # Constants.hs:10-13 (DELTA = 7^(2^32))
+ROOT_OF_UNITY = pow(MULTIPLICATIVE_GENERATOR, (R_MOD - 1) >> TWO_ADICITY, R_MOD)
+# a primitive cube root of unity; upstream's coset generator (F::ZETA) is one of the two --
+# which one is not verifiable here, so EvaluationDomain takes g_coset as a parameter
+ZETA = pow(MULTIPLICATIVE_GENERATOR, (R_MOD - 1) // 3, R_MOD)
+
+
+def fr_bytes(x: int) -> bytes:
+    return (x % R_MOD).to_bytes(32, "little")
+
+
+class ParamsKZG:
+    """Device-resident SRS: ``g`` (monomial basis) and ``g_lagrange`` (Lagrange basis) tables.
+
+    Mirrors the two base tables of upstream ``ParamsKZG<Bls12>`` that
+    ``get_or_create_kzg_params`` returns (/root/reference/src/kzg_params.rs:33-47)."""
+
+    def __init__(self, k: int, g: bytes, g_lagrange: Optional[bytes] = None, fmt: int = FMT_CANONICAL,
+                 stride: int = 96):
+        self.k = k
+        self.n = 1 << k
+        self._g = self._register(g, fmt, stride)
+        self._g_lagrange = self._register(g_lagrange, fmt, stride) if g_lagrange is not None else None
+
+    def _register(self, table: bytes, fmt: int, stride: int) -> int:
+        if len(table) < (self.n - 1) * stride + 96:
+            raise ValueError("SRS table shorter than 2^k points")
+        h = C.c_uint64(0)
+        check(lib().b200zk_bases_register(addr(table), self.n, fmt, stride, C.byref(h)))
+        return h.value
+
+    @classmethod
+    def from_device(cls, k: int, d_g: int, d_g_lagrange: Optional[int] = None, fmt: int = capi.FMT_MONT):
+        """Adopt tables that already live in HBM (e.g. produced by the synthetic generator)."""
+        self = cls.__new__(cls)
+        self.k, self.n = k, 1 << k
+        h = C.c_uint64(0)
+        check(lib().b200zk_bases_register_dev(d_g, self.n, fmt, 96, C.byref(h)))
+        self._g = h.value
+        self._g_lagrange = None
+        if d_g_lagrange is not None:
+            check(lib().b200zk_bases_register_dev(d_g_lagrange, self.n, fmt, 96, C.byref(h)))
+            self._g_lagrange = h.value
+        return self
+
+    def release(self) -> None:
+        for h in (self._g, self._g_lagrange):
+            if h:
+                check(lib().b200zk_bases_release(h))
+        self._g = self._g_lagrange = None
+
+
+class KZGCommitmentScheme:
+    """``commit`` / ``commit_lagrange`` of upstream ``KZGCommitmentScheme<Bls12>``: one G1 MSM of
+    the polynomial's n coefficients (or evaluations) against the matching SRS table.  Like
+    upstream, a polynomial longer than the table is a programming error (asserted)."""
+
+    @staticmethod
+    def _msm(handle: int, n_max: int, poly: bytes, batch: int = 1) -> List[bytes]:
+        if len(poly) % (32 * batch):
+            raise ValueError("polynomial bytes must be batch * n * 32")
+        n = len(poly) // (32 * batch)
+        assert n <= n_max, "polynomial longer than the SRS"
+        out = C.create_string_buffer(96 * batch)
+        check(lib().b200zk_msm_g1_batch(handle, 0, addr(poly), n, batch, FMT_CANONICAL, addr(out)))
+        return [out.raw[96 * i:96 * (i + 1)] for i in range(batch)]
+
+    @staticmethod
+    def commit(params: ParamsKZG, poly: bytes) -> bytes:
+        return KZGCommitmentScheme._msm(params._g, params.n, poly)[0]
+
+    @staticmethod
+    def commit_lagrange(params: ParamsKZG, poly: bytes) -> bytes:
+        if params._g_lagrange is None:
+            raise ValueError("params were built without a Lagrange-basis table")
+        return KZGCommitmentScheme._msm(params._g_lagrange, params.n, poly)[0]
+
+    @staticmethod
+    def commit_batch(params: ParamsKZG, polys: Sequence[bytes], lagrange: bool = False) -> List[bytes]:
+        """All columns of one prover phase in a single launch sequence (same length each)."""
+        if not polys:
+            return []
+        h = params._g_lagrange if lagrange else params._g
+        if h is None:
+            raise ValueError("params were built without a Lagrange-basis table")
+        return KZGCommitmentScheme._msm(h, params.n, b"".join(polys), batch=len(polys))
+
+
+class EvaluationDomain:
+    """Mirror of upstream ``EvaluationDomain::new(j, k)``: n = 2^k rows, quotient degree j - 1,
+    extended domain of size 2^extended_k with extended_k = k + ceil(log2(j - 1)); omega follows
+    the convention pinned at /root/reference/aiken-verifier/aiken_halo2/lib/omega_rotations.ak:48-81."""
+
+    def __init__(self, j: int, k: int, g_coset: int = ZETA):
+        self.k = k
+        self.n = 1 << k
+        self.quotient_poly_degree = j - 1
+        ext = k
+        while (1 << ext) < self.n * self.quotient_poly_degree:
+            ext += 1
+        if ext > TWO_ADICITY:
+            raise ValueError("extended_k exceeds the 2-adicity of the field")
+        self.extended_k = ext
+        self.omega = pow(ROOT_OF_UNITY, 1 << (TWO_ADICITY - k), R_MOD)
+        self.omega_inv = pow(self.omega, R_MOD - 2, R_MOD)
+        self.extended_omega = pow(ROOT_OF_UNITY, 1 << (TWO_ADICITY - ext), R_MOD)
+        self.extended_omega_inv = pow(self.extended_omega, R_MOD - 2, R_MOD)
+        self.g_coset = g_coset % R_MOD
+        self.g_coset_inv = pow(self.g_coset, R_MOD - 2, R_MOD)
+
+    def get_omega(self) -> int:
+        return self.omega
+
+    def get_omega_inv(self) -> int:
+        return self.omega_inv
+
+    def get_extended_omega(self) -> int:
+        return self.extended_omega
+
+    @staticmethod
+    def _ntt(data: bytearray, log_n: int, omega: int, flags: int, shift: Optional[int] = None, batch: int = 1):
+        sh = fr_bytes(shift) if shift is not None else None
+        check(lib().b200zk_ntt_fr_batch(addr(data), batch, log_n, addr(fr_bytes(omega)), flags, addr(sh)))
+
+    def lagrange_to_coeff(self, a: bytes) -> bytes:
+        """Evaluations over H (n values) -> coefficients (inverse NTT, scaled by 1/n)."""
+        assert len(a) == 32 * self.n
+        buf = bytearray(a)
+        self._ntt(buf, self.k, self.omega_inv, NTT_INVERSE_SCALE)
+        return bytes(buf)
+
+    def coeff_to_lagrange(self, a: bytes) -> bytes:
+        assert len(a) == 32 * self.n
+        buf = bytearray(a)
+        self._ntt(buf, self.k, self.omega, 0)
+        return bytes(buf)
+
+    def coeff_to_extended(self, a: bytes) -> bytes:
+        """n coefficients -> evaluations over the coset g_coset * H_ext (zero-padded, scaled by
+        g_coset^i, forward NTT of size 2^extended_k)."""
+        assert len(a) == 32 * self.n
+        buf = bytearray(a) + bytearray(32 * ((1 << self.extended_k) - self.n))
+        self._ntt(buf, self.extended_k, self.extended_omega, NTT_COSET_IN, self.g_coset)
+        return bytes(buf)
+
+    def extended_to_coeff(self, a: bytes) -> bytes:
+        """Inverse of coeff_to_extended; returns the n * (j - 1) low coefficients like upstream."""
+        assert len(a) == 32 << self.extended_k
+        buf = bytearray(a)
+        self._ntt(buf, self.extended_k, self.extended_omega_inv, NTT_INVERSE_SCALE | NTT_COSET_OUT, self.g_coset_inv)
+        return bytes(buf[: 32 * self.n * self.quotient_poly_degree])
+
+    def lagrange_to_coeff_batch(self, polys: Sequence[bytes]) -> List[bytes]:
+        buf = bytearray(b"".join(polys))
+        self._ntt(buf, self.k, self.omega_inv, NTT_INVERSE_SCALE, batch=len(polys))
+        step = 32 * self.n
+        return [bytes(buf[i * step:(i + 1) * step]) for i in range(len(polys))]
+
+
+class DualMSM:
+    """The verifier's pair of lazy MSMs (upstream ``DualMSM``; restated in-tree at
+    /root/reference/aiken-verifier/aiken_halo2/lib/halo2_kzg.ak:15-44 and
+    /root/reference/plinth-verifier/plutus-halo2/src/Plutus/Crypto/Halo2/Halo2MultiOpenMSM.hs:60-98).
+
+    ``eval`` evaluates both sums on the GPU.  The accept decision is
+    ``e(left, [s]G2) == e(right, G2)`` (/root/reference/aiken-verifier/templates/verification_h2.hbs:121-128);
+    the pairing itself stays with the caller's pairing library and is out of this path's scope."""
+
+    def __init__(self):
+        self.left: List[Tuple[int, bytes]] = []
+        self.right: List[Tuple[int, bytes]] = []
+
+    def append_left(self, scalar: int, point: bytes) -> None:
+        self.left.append((scalar % R_MOD, point))
+
+    def append_right(self, scalar: int, point: bytes) -> None:
+        self.right.append((scalar % R_MOD, point))
+
+    def scale(self, factor: int) -> None:
+        self.left = [(s * factor % R_MOD, p) for s, p in self.left]
+        self.right = [(s * factor % R_MOD, p) for s, p in self.right]
+
+    def add_msm(self, other: "DualMSM") -> None:
+        """batch_verify's random linear combination appends the other guard's terms
+        (/root/reference/src/circuits/schnorr_circuit.rs:224)."""
+        self.left += other.left
+        self.right += other.right
+
+    @staticmethod
+    def _eval(terms: List[Tuple[int, bytes]]) -> bytes:
+        out = C.create_string_buffer(96)
+        if not terms:
+            return out.raw
+        pts = b"".join(p for _, p in terms)
+        sc = b"".join(fr_bytes(s) for s, _ in terms)
+        check(lib().b200zk_msm_g1_adhoc(addr(pts), FMT_CANONICAL, addr(sc), FMT_CANONICAL, len(terms), addr(out)))
+        return out.raw
+
+    def eval(self) -> Tuple[bytes, bytes]:
+        return self._eval(self.left), self._eval(self.right)
+
+
+def g1_compress(affine: bytes) -> bytes:
+    """48-byte ZCash compressed form, what the transcript absorbs
+    (/root/reference/aiken-verifier/aiken_halo2/lib/transcript.ak:62-83)."""
+    out = C.create_string_buffer(48)
+    check(lib().b200zk_g1_compress(addr(affine), addr(out)))
+    return out.raw
