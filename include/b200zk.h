@@ -138,9 +138,11 @@ int32_t b200zk_g1_synth_bases_dev(uint64_t seed, uint64_t start, uint64_t n, voi
  * op 0 mul, 1 add, 2 sub, 3 inverse(a); field 0 = Fr (32 B), 1 = Fp (48 B); canonical in/out.    */
 int32_t b200zk_selftest_field(uint32_t field, uint32_t op, const uint8_t *a, const uint8_t *b, uint8_t *out,
                               uint64_t count);
-/* integer-pipe micro-benchmark: kind 0 = IMAD.WIDE.U32 chains, 1 = IMAD lo+hi pairs, 2 = Fp Montgomery
- * multiplications, 3 = XYZZ mixed additions, 4 = Fr multiplications.  *out_ops_per_s receives
- * limb-MACs (kinds 0,1), multiplications (2,4) or additions (3) per second over all SMs.           */
+/* integer-pipe micro-benchmark: kind 0 = independent IMAD.WIDE.U32, 1 = IMAD lo+hi pairs, 2 = Fp Montgomery
+ * multiplications, 3 = XYZZ mixed additions, 4 = Fr multiplications, 5 = carry-chained IMAD.WIDE.U32.X rows
+ * (as the Montgomery multiplier issues them), 6 = DFMA, 7 = IMAD.WIDE with carry-out only, 8 = IMAD.WIDE
+ * paired 1:1 with IADD.  *out_ops_per_s receives limb-MACs (0,1,5,7,8), multiplications (2,4), additions (3)
+ * or FMAs (6) per second over all SMs.                                                            */
 int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double *out_ops_per_s, double *out_ms);
 /* number of kernels this library has launched since init (bench.py's gpu_launches counter) */
 uint64_t b200zk_launch_count(void);

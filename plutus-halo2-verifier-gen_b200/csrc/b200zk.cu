@@ -471,6 +471,89 @@ __global__ void __launch_bounds__(256) mb_imad_pair_kernel(uint64_t* out, uint32
     for (int k = 0; k < 8; k++) s ^= ((uint64_t)hi[k] << 32) | lo[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+
+// carry-chained rows exactly as fe_mul issues them: 4 independent rows of 6 IMAD.WIDE.U32.X
+__global__ void __launch_bounds__(256) mb_imad_chain_kernel(uint64_t* out, uint32_t iters, uint32_t a0, uint32_t b0) {
+    uint32_t acc[4][12];
+    uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int k = 0; k < 12; k++) acc[r][k] = r * 12 + k;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            mad_wide_cc(acc[r][0], acc[r][1], a, b, acc[r][0], acc[r][1]);
+#pragma unroll
+            for (int k = 2; k < 12; k += 2) madc_wide_cc(acc[r][k], acc[r][k + 1], a, b, acc[r][k], acc[r][k + 1]);
+        }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int k = 0; k < 12; k++) s = s * 31 + acc[r][k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// every wide MAD produces a carry-out but takes no carry-in
+__global__ void __launch_bounds__(256) mb_imad_cout_kernel(uint64_t* out, uint32_t iters, uint32_t a0, uint32_t b0) {
+    uint32_t lo[8], hi[8];
+    uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { lo[k] = k; hi[k] = k + 1; }
+    uint32_t sink = 0;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) mad_wide_cc(lo[k], hi[k], a, b, lo[k], hi[k]);
+        }
+        sink = addc(sink, 0);
+    }
+    uint64_t s = sink;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= ((uint64_t)hi[k] << 32) | lo[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) mb_dfma_kernel(uint64_t* out, uint32_t iters, double a0, double b0) {
+    double acc[8];
+    double a = a0 + threadIdx.x * 1e-9, b = b0 + blockIdx.x * 1e-9;
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = k;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc[k]) : "d"(a), "d"(b));
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += acc[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (uint64_t)__double_as_longlong(s);
+}
+// one IADD3 (ALU pipe) per IMAD.WIDE (FMA pipe): do the two pipes issue side by side?
+__global__ void __launch_bounds__(256) mb_imad_alu_kernel(uint64_t* out, uint32_t iters, uint32_t a0, uint32_t b0) {
+    uint64_t acc[8];
+    uint32_t x[8];
+    uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { acc[k] = k; x[k] = k * 3; }
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(x[k]) : "r"(a));
+            }
+        }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= acc[k] + x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 template <class P>
 __global__ void __launch_bounds__(256) mb_femul_kernel(uint32_t* out, uint32_t iters) {
     Fe<P> x = fe_one<P>(), y = fe_one<P>();
@@ -831,7 +914,7 @@ int32_t b200zk_selftest_field(uint32_t field, uint32_t op, const uint8_t* a, con
 int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double* out_ops_per_s, double* out_ms) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(need_init());
-    if (kind > 4 || !out_ops_per_s) return fail(B200ZK_ERR_INVALID_ARG, "bad microbench arguments");
+    if (kind > 8 || !out_ops_per_s) return fail(B200ZK_ERR_INVALID_ARG, "bad microbench arguments");
     int sms = g.prop.multiProcessorCount;
     unsigned threads = (kind == 3) ? 128 : 256;
     unsigned blocks = (unsigned)sms * ((kind == 3) ? 3 : ((kind == 2) ? 4 : 8));
@@ -861,9 +944,25 @@ int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double* out_ops_per_s, 
                 LAUNCH(mb_madd_kernel, blocks, threads, 0, g.stream, (const uint32_t*)d_gen, g.stage.as<uint32_t>(), iters);
                 per_thread = 1.0 * iters;
                 break;
-            default:
+            case 4:
                 LAUNCH(mb_femul_kernel<FrParams>, blocks, threads, 0, g.stream, g.stage.as<uint32_t>(), iters);
                 per_thread = 2.0 * iters;
+                break;
+            case 5:
+                LAUNCH(mb_imad_chain_kernel, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
+                per_thread = 24.0 * iters;
+                break;
+            case 6:
+                LAUNCH(mb_dfma_kernel, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 1.000001, 0.999999);
+                per_thread = 32.0 * iters;
+                break;
+            case 7:
+                LAUNCH(mb_imad_cout_kernel, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
+                per_thread = 24.0 * iters;
+                break;
+            default:
+                LAUNCH(mb_imad_alu_kernel, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
+                per_thread = 32.0 * iters;
                 break;
         }
         CU(cudaEventRecord(e1, g.stream));

@@ -151,7 +151,8 @@ class EvaluationDomain:
     @staticmethod
     def _ntt(data: bytearray, log_n: int, omega: int, flags: int, shift: Optional[int] = None, batch: int = 1):
         sh = fr_bytes(shift) if shift is not None else None
-        check(lib().b200zk_ntt_fr_batch(addr(data), batch, log_n, addr(fr_bytes(omega)), flags, addr(sh)))
+        om = fr_bytes(omega)  # named so the buffer outlives the call
+        check(lib().b200zk_ntt_fr_batch(addr(data), batch, log_n, addr(om), flags, addr(sh)))
 
     def lagrange_to_coeff(self, a: bytes) -> bytes:
         """Evaluations over H (n values) -> coefficients (inverse NTT, scaled by 1/n)."""

@@ -59,10 +59,11 @@ def test_no_gpu_fails_loudly(zk):
     assert ei.value.code == -3 and "no CPU fallback" in str(ei.value)
     # compute entry points refuse to run without an initialised device
     out = C.create_string_buffer(96)
-    rc = zk.lib().b200zk_msm_g1(1, 0, zk.capi.addr(bytes(32)), 1, 0, zk.capi.addr(out))
+    zero = bytes(32)
+    rc = zk.lib().b200zk_msm_g1(1, 0, zk.capi.addr(zero), 1, 0, zk.capi.addr(out))
     assert rc == -6
     data = bytearray(64)
-    rc = zk.lib().b200zk_ntt_fr(zk.capi.addr(data), 1, zk.capi.addr(bytes(32)), 0, 0)
+    rc = zk.lib().b200zk_ntt_fr(zk.capi.addr(data), 1, zk.capi.addr(zero), 0, 0)
     assert rc == -6
     with pytest.raises(zk.B200zkError):
         zk.host.KZGCommitmentScheme._msm(1, 4, bytes(128))

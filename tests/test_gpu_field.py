@@ -38,6 +38,6 @@ def test_field_ops_match_oracle(gpu, pyref, oracle, field, size, mod_name):
 
 def test_microbench_runs(gpu):
     ops, ms = C.c_double(), C.c_double()
-    for kind in range(5):
+    for kind in range(9):
         gpu.capi.check(gpu.lib().b200zk_microbench(kind, 200, C.byref(ops), C.byref(ms)))
         assert ops.value > 0

@@ -15,8 +15,10 @@ def fr(x):
 
 def gpu_ntt(gpu, data: bytes, log_n, omega, flags=0, shift=None, batch=1) -> bytes:
     buf = bytearray(data)
-    gpu.capi.check(gpu.lib().b200zk_ntt_fr_batch(gpu.capi.addr(buf), batch, log_n, gpu.capi.addr(fr(omega)), flags,
-                                                 gpu.capi.addr(fr(shift)) if shift is not None else 0))
+    wb = fr(omega)                                   # keep the byte strings alive across the call
+    sb = fr(shift) if shift is not None else None
+    gpu.capi.check(gpu.lib().b200zk_ntt_fr_batch(gpu.capi.addr(buf), batch, log_n, gpu.capi.addr(wb), flags,
+                                                 gpu.capi.addr(sb)))
     return bytes(buf)
 
 
@@ -127,7 +129,8 @@ def test_evaluation_domain_mirror(gpu, oracle, pyref):
 
 def test_argument_errors(gpu):
     data = bytearray(64)
+    one = fr(1)
     L = gpu.lib()
-    assert L.b200zk_ntt_fr(gpu.capi.addr(data), 40, gpu.capi.addr(fr(1)), 0, 0) == -1
-    assert L.b200zk_ntt_fr(gpu.capi.addr(data), 1, gpu.capi.addr(fr(1)), gpu.NTT_COSET_IN, 0) == -1
-    assert L.b200zk_ntt_fr(0, 1, gpu.capi.addr(fr(1)), 0, 0) == -1
+    assert L.b200zk_ntt_fr(gpu.capi.addr(data), 40, gpu.capi.addr(one), 0, 0) == -1
+    assert L.b200zk_ntt_fr(gpu.capi.addr(data), 1, gpu.capi.addr(one), gpu.NTT_COSET_IN, 0) == -1
+    assert L.b200zk_ntt_fr(0, 1, gpu.capi.addr(one), 0, 0) == -1

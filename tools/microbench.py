@@ -12,11 +12,12 @@ zk = importlib.import_module("plutus-halo2-verifier-gen_b200")
 
 def run(iters=2000):
     zk.init(-1)
-    names = {0: "imad_wide_lmac_per_s", 1: "imad_lohi_lmac_per_s", 2: "fp_mul_per_s", 3: "xyzz_madd_per_s", 4: "fr_mul_per_s"}
+    names = {0: "imad_wide_lmac_per_s", 1: "imad_lohi_lmac_per_s", 2: "fp_mul_per_s", 3: "xyzz_madd_per_s", 4: "fr_mul_per_s",
+             5: "imad_wide_carry_chain_lmac_per_s", 6: "dfma_per_s", 7: "imad_wide_carry_out_lmac_per_s", 8: "imad_wide_plus_iadd_lmac_per_s"}
     out = {"device": zk.device_info()}
     for kind, name in names.items():
         ops, ms = C.c_double(), C.c_double()
-        it = iters * (8 if kind < 2 else 1)
+        it = iters * (1 if kind in (2, 3, 4) else 8)
         zk.capi.check(zk.lib().b200zk_microbench(kind, it, C.byref(ops), C.byref(ms)))
         out[name] = ops.value
         out[name.replace("_per_s", "_ms")] = ms.value
