@@ -146,6 +146,12 @@ int32_t b200zk_selftest_field(uint32_t field, uint32_t op, const uint8_t *a, con
 int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double *out_ops_per_s, double *out_ms);
 /* number of kernels this library has launched since init (bench.py's gpu_launches counter) */
 uint64_t b200zk_launch_count(void);
+/* Phase timing of the last MSM / NTT call, taken with CUDA events on the launching stream (no effect on the
+ * work itself).  kind: 1 = MSM with phases {sort (digits, scan, scatter, tasks), accumulate, tail (collapse,
+ * bucket reduce, window combine)}; 2 = NTT with one phase per pass.  Synchronises on the last event.        */
+int32_t b200zk_set_profiling(uint32_t enable);
+int32_t b200zk_get_profile(uint32_t *kind, double *phase_ms, uint32_t cap, uint32_t *n_phases, uint32_t *msm_window_bits,
+                           uint32_t *msm_windows);
 /* overrides for experiments: MSM window bits (0 = automatic) and max entries per task (0 = automatic) */
 int32_t b200zk_set_msm_tuning(uint32_t window_bits, uint32_t smax);
 

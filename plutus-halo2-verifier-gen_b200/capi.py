@@ -64,6 +64,9 @@ SIGNATURES = {
     "b200zk_microbench": (C.c_int32, [C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b200zk_launch_count": (C.c_uint64, []),
     "b200zk_set_msm_tuning": (C.c_int32, [C.c_uint32, C.c_uint32]),
+    "b200zk_set_profiling": (C.c_int32, [C.c_uint32]),
+    "b200zk_get_profile": (C.c_int32, [C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_uint32, C.POINTER(C.c_uint32),
+                                       C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 }
 
 
@@ -131,3 +134,19 @@ def device_info() -> str:
 
 def launch_count() -> int:
     return int(lib().b200zk_launch_count())
+
+
+def set_profiling(enable: bool) -> None:
+    check(lib().b200zk_set_profiling(1 if enable else 0))
+
+
+def get_profile() -> dict:
+    """Phase times (ms) of the last MSM / NTT call, measured with CUDA events on its stream."""
+    kind, n, c, w = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    ms = (C.c_double * 8)()
+    check(lib().b200zk_get_profile(C.byref(kind), ms, 8, C.byref(n), C.byref(c), C.byref(w)))
+    phases = [ms[i] for i in range(n.value)]
+    if kind.value == 1:
+        names = ["sort", "accumulate", "tail"]
+        return {"kind": "msm", "window_bits": c.value, "windows": w.value, **dict(zip(names, phases))}
+    return {"kind": "ntt", "passes": phases}

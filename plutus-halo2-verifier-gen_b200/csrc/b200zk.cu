@@ -112,6 +112,12 @@ struct Ctx {
     std::map<CosetKey, uint32_t*> coset_tables;
     uint32_t* fixed_table = nullptr;  // 8 x 256 multiples of G for the synthetic-base generator
     uint32_t tune_c = 0, tune_smax = 0;
+    // phase timing (b200zk_set_profiling): events recorded on the launching stream
+    bool profiling = false;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int ev_count = 0;   // events recorded by the last profiled call
+    int ev_kind = 0;    // 1 = msm, 2 = ntt
+    MsmPlan last_plan{};
     // MSM workspace
     DevBuf scalars, counts, offsets, cursor, ntask, task_off, entries, task_bucket, task_start, task_len, buckets,
         partials, redS[2], redA[2], scan_tmp[2], out_mont, out_canon, stage, flag;
@@ -119,6 +125,14 @@ struct Ctx {
     DevBuf ntt_data, ntt_tmp[2], small;
 };
 Ctx g;
+
+int32_t prof_mark(int idx, cudaStream_t s) {
+    if (!g.profiling) return B200ZK_OK;
+    if (!g.ev[idx]) CU(cudaEventCreate(&g.ev[idx]));
+    CU(cudaEventRecord(g.ev[idx], s));
+    g.ev_count = idx + 1;
+    return B200ZK_OK;
+}
 
 int32_t need_init() {
     if (!g.inited) return fail(B200ZK_ERR_NOT_INIT, "b200zk_init has not been called (or failed): no CUDA device is bound");
@@ -219,6 +233,8 @@ int32_t msm_run(const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, 
     uint32_t* buckets = g.buckets.as<uint32_t>();
     uint32_t* partials = g.partials.as<uint32_t>();
 
+    g.ev_kind = 1;
+    TRY(prof_mark(0, s));
     CU(cudaMemsetAsync(counts, 0, (NBt + 1) * 4, s));
     CU(cudaMemsetAsync(ntask, 0, (NBt + 1) * 4, s));
     dim3 dgrid((unsigned)((n + 255) / 256), batch);
@@ -235,9 +251,11 @@ int32_t msm_run(const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, 
            (const uint32_t*)task_off, NBt, pl.smax, g.task_bucket.as<uint32_t>(), g.task_start.as<uint32_t>(),
            g.task_len.as<uint32_t>());
     CU(cudaMemsetAsync(buckets, 0, NBt * 192, s));
+    TRY(prof_mark(1, s));
     LAUNCH(msm_accumulate_kernel, (unsigned)((max_tasks + 127) / 128), 128, 0, s, d_bases, (const uint32_t*)entries,
            (const uint32_t*)g.task_bucket.as<uint32_t>(), (const uint32_t*)g.task_start.as<uint32_t>(),
            (const uint32_t*)g.task_len.as<uint32_t>(), (const uint32_t*)(task_off + NBt), buckets, partials);
+    TRY(prof_mark(2, s));
     LAUNCH(msm_collapse_kernel, (unsigned)((NBt + 3) / 4), 128, 0, s, (const uint32_t*)ntask, (const uint32_t*)task_off,
            NBt, (const uint32_t*)partials, buckets);
 
@@ -262,6 +280,8 @@ int32_t msm_run(const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, 
         pp ^= 1;
     } while (m > 1);
     LAUNCH(msm_combine_kernel, batch, 32, 0, s, win_sums, pl.W, pl.c, d_out_mont, d_out_canon);
+    TRY(prof_mark(3, s));
+    g.last_plan = pl;
     return B200ZK_OK;
 }
 
@@ -388,6 +408,8 @@ int32_t ntt_run(uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t 
     }
     uint32_t log_s = 0;
     const uint32_t* src = d_data;
+    g.ev_kind = 2;
+    TRY(prof_mark(0, s));
     for (uint32_t i = 0; i < pl->npass; i++) {
         bool last = (i + 1 == pl->npass);
         uint32_t* dst = last ? d_data : bufs[i & 1];
@@ -409,6 +431,7 @@ int32_t ntt_run(uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t 
         a.total_cols = (uint64_t)batch << a.log_cols;
         uint64_t ctas = (total + NTT_B - 1) / NTT_B;
         LAUNCH(ntt_pass_kernel, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+        TRY(prof_mark((int)i + 1, s));
         src = dst;
         log_s += pl->deg[i];
     }
@@ -435,15 +458,17 @@ __global__ void selftest_kernel(const uint32_t* a, const uint32_t* b, uint32_t* 
 }
 
 __global__ void __launch_bounds__(256) mb_imad_wide_kernel(uint64_t* out, uint32_t iters, uint32_t a0, uint32_t b0) {
+    // plain IMAD.WIDE.U32 (no carry in or out); the multiplicand rotates through the other
+    // accumulators so that ptxas cannot hoist the product out of the loop
     uint64_t acc[8];
-    uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
+    uint32_t b = b0 + blockIdx.x;
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = k;
+    for (int k = 0; k < 8; k++) acc[k] = a0 + threadIdx.x * 8 + k;
     for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
         for (int r = 0; r < 4; r++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
+            for (int k = 0; k < 8; k++) acc[k] = (uint64_t)(uint32_t)acc[(k + 1) & 7] * b + acc[k];
         }
     }
     uint64_t s = 0;
@@ -532,20 +557,20 @@ __global__ void __launch_bounds__(256) mb_dfma_kernel(uint64_t* out, uint32_t it
     for (int k = 0; k < 8; k++) s += acc[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = (uint64_t)__double_as_longlong(s);
 }
-// one IADD3 (ALU pipe) per IMAD.WIDE (FMA pipe): do the two pipes issue side by side?
+// one LOP3 (ALU pipe) per IMAD.WIDE (FMA pipe): do the two pipes issue side by side?
 __global__ void __launch_bounds__(256) mb_imad_alu_kernel(uint64_t* out, uint32_t iters, uint32_t a0, uint32_t b0) {
     uint64_t acc[8];
     uint32_t x[8];
-    uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
+    uint32_t b = b0 + blockIdx.x;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { acc[k] = k; x[k] = k * 3; }
+    for (int k = 0; k < 8; k++) { acc[k] = a0 + threadIdx.x * 8 + k; x[k] = k * 3; }
     for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
         for (int r = 0; r < 4; r++) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
-                asm volatile("add.u32 %0, %0, %1;" : "+r"(x[k]) : "r"(a));
+                acc[k] = (uint64_t)(uint32_t)acc[(k + 1) & 7] * b + acc[k];
+                x[k] = (x[k] ^ x[(k + 3) & 7]) & ~x[(k + 5) & 7];
             }
         }
     }
@@ -978,6 +1003,33 @@ int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double* out_ops_per_s, 
 }
 
 uint64_t b200zk_launch_count(void) { return g_launches.load(); }
+
+int32_t b200zk_set_profiling(uint32_t enable) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.profiling = enable != 0;
+    g.ev_count = 0;
+    return B200ZK_OK;
+}
+
+int32_t b200zk_get_profile(uint32_t* kind, double* phase_ms, uint32_t cap, uint32_t* n_phases, uint32_t* msm_window_bits,
+                           uint32_t* msm_windows) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(need_init());
+    if (!kind || !phase_ms || !n_phases) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    *kind = (uint32_t)g.ev_kind;
+    *n_phases = 0;
+    if (msm_window_bits) *msm_window_bits = g.last_plan.c;
+    if (msm_windows) *msm_windows = g.last_plan.W;
+    if (g.ev_count < 2) return B200ZK_OK;
+    CU(cudaEventSynchronize(g.ev[g.ev_count - 1]));
+    for (int i = 0; i + 1 < g.ev_count && (uint32_t)i < cap; i++) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, g.ev[i], g.ev[i + 1]));
+        phase_ms[i] = ms;
+        *n_phases = (uint32_t)i + 1;
+    }
+    return B200ZK_OK;
+}
 
 int32_t b200zk_set_msm_tuning(uint32_t window_bits, uint32_t smax) {
     std::lock_guard<std::mutex> lk(g_mu);
