@@ -1,0 +1,132 @@
+// b200zk.hpp -- header-only C++ mirror of the reference-facing interface for the MSM / NTT path,
+// layered on the C ABI of b200zk.h.  It marshals buffers and nothing else (no arithmetic, no
+// fallback).  Names and argument meaning follow the upstream traits the reference reaches:
+//   ParamsKZG                        /root/reference/src/kzg_params.rs:33-80
+//   KZGCommitmentScheme::commit*     /root/reference/examples/simple_mul.rs:62,72 (via keygen_vk / create_proof)
+//   EvaluationDomain                 /root/reference/examples/ivc.rs:109, /root/reference/src/circuits/ivc_circuit.rs:305
+//   DualMSM (Guard::verify)          /root/reference/examples/simple_mul.rs:98-102
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "b200zk.h"
+
+namespace b200zk {
+
+struct Error : std::runtime_error {
+    int32_t code;
+    Error(int32_t c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int32_t rc) {
+    if (rc == B200ZK_OK) return;
+    char buf[1024] = {0};
+    b200zk_last_error(buf, sizeof buf);
+    throw Error(rc, buf);
+}
+
+using Fr = std::array<uint8_t, 32>;        // little-endian canonical
+using G1Affine = std::array<uint8_t, 96>;  // x || y little-endian canonical, identity = (0,0)
+
+inline void init(int device = -1) { check(b200zk_init(device)); }
+
+// Device residency of the two SRS tables (g: monomial basis, g_lagrange: Lagrange basis).
+class ParamsKZG {
+public:
+    ParamsKZG(uint32_t k, const uint8_t* g, const uint8_t* g_lagrange, uint32_t fmt = B200ZK_FMT_CANONICAL,
+              uint32_t stride = 96)
+        : k_(k), n_(uint64_t(1) << k) {
+        check(b200zk_bases_register(g, n_, fmt, stride, &g_));
+        if (g_lagrange) check(b200zk_bases_register(g_lagrange, n_, fmt, stride, &gl_));
+    }
+    ~ParamsKZG() {
+        if (g_) b200zk_bases_release(g_);
+        if (gl_) b200zk_bases_release(gl_);
+    }
+    ParamsKZG(const ParamsKZG&) = delete;
+    ParamsKZG& operator=(const ParamsKZG&) = delete;
+    uint32_t k() const { return k_; }
+    uint64_t n() const { return n_; }
+    uint64_t g() const { return g_; }
+    uint64_t g_lagrange() const { return gl_; }
+
+private:
+    uint32_t k_;
+    uint64_t n_, g_ = 0, gl_ = 0;
+};
+
+struct KZGCommitmentScheme {
+    // commit to a polynomial in coefficient form: MSM against params.g
+    static G1Affine commit(const ParamsKZG& params, const std::vector<Fr>& poly) { return msm(params.g(), params.n(), poly); }
+    // commit to a polynomial in Lagrange form: MSM against params.g_lagrange
+    static G1Affine commit_lagrange(const ParamsKZG& params, const std::vector<Fr>& poly) {
+        if (!params.g_lagrange()) throw Error(B200ZK_ERR_INVALID_ARG, "params built without a Lagrange-basis table");
+        return msm(params.g_lagrange(), params.n(), poly);
+    }
+
+private:
+    static G1Affine msm(uint64_t handle, uint64_t n_max, const std::vector<Fr>& poly) {
+        if (poly.size() > n_max) throw Error(B200ZK_ERR_INVALID_ARG, "polynomial longer than the SRS");
+        G1Affine out{};
+        check(b200zk_msm_g1(handle, 0, reinterpret_cast<const uint8_t*>(poly.data()), poly.size(), B200ZK_FMT_CANONICAL,
+                            out.data()));
+        return out;
+    }
+};
+
+// The four transforms of the halo2 evaluation domain.  Domain constants (omega, its inverse, the
+// extended omega and the coset generator) are Fr values the caller already has (upstream computes
+// them in EvaluationDomain::new); they are passed in canonical form.
+class EvaluationDomain {
+public:
+    EvaluationDomain(uint32_t k, uint32_t extended_k, Fr omega, Fr omega_inv, Fr extended_omega, Fr extended_omega_inv,
+                     Fr g_coset, Fr g_coset_inv, uint32_t quotient_poly_degree)
+        : k_(k), ek_(extended_k), w_(omega), wi_(omega_inv), ew_(extended_omega), ewi_(extended_omega_inv), g_(g_coset),
+          gi_(g_coset_inv), qd_(quotient_poly_degree) {}
+
+    void lagrange_to_coeff(std::vector<Fr>& a) const { run(a, k_, wi_, B200ZK_NTT_INVERSE_SCALE, nullptr); }
+    void coeff_to_lagrange(std::vector<Fr>& a) const { run(a, k_, w_, 0, nullptr); }
+    void coeff_to_extended(std::vector<Fr>& a) const {
+        a.resize(size_t(1) << ek_, Fr{});
+        run(a, ek_, ew_, B200ZK_NTT_COSET_IN, g_.data());
+    }
+    void extended_to_coeff(std::vector<Fr>& a) const {
+        run(a, ek_, ewi_, B200ZK_NTT_INVERSE_SCALE | B200ZK_NTT_COSET_OUT, gi_.data());
+        a.resize((size_t(1) << k_) * qd_);
+    }
+
+private:
+    static void run(std::vector<Fr>& a, uint32_t log_n, const Fr& omega, uint32_t flags, const uint8_t* shift) {
+        if (a.size() != (size_t(1) << log_n)) throw Error(B200ZK_ERR_INVALID_ARG, "polynomial length is not the domain size");
+        check(b200zk_ntt_fr(reinterpret_cast<uint8_t*>(a.data()), log_n, omega.data(), flags, shift));
+    }
+    uint32_t k_, ek_;
+    Fr w_, wi_, ew_, ewi_, g_, gi_;
+    uint32_t qd_;
+};
+
+// The verifier's pair of lazy MSMs; eval() returns (left, right).  The accept decision
+// e(left, [s]G2) == e(right, G2) (/root/reference/aiken-verifier/templates/verification_h2.hbs:121-128)
+// stays with the caller's pairing library.
+class DualMSM {
+public:
+    void append_left(const Fr& s, const G1Affine& p) { ls_.push_back(s); lp_.push_back(p); }
+    void append_right(const Fr& s, const G1Affine& p) { rs_.push_back(s); rp_.push_back(p); }
+    std::pair<G1Affine, G1Affine> eval() const { return {one(ls_, lp_), one(rs_, rp_)}; }
+
+private:
+    static G1Affine one(const std::vector<Fr>& s, const std::vector<G1Affine>& p) {
+        G1Affine out{};
+        if (s.empty()) return out;
+        check(b200zk_msm_g1_adhoc(reinterpret_cast<const uint8_t*>(p.data()), B200ZK_FMT_CANONICAL,
+                                  reinterpret_cast<const uint8_t*>(s.data()), B200ZK_FMT_CANONICAL, s.size(), out.data()));
+        return out;
+    }
+    std::vector<Fr> ls_, rs_;
+    std::vector<G1Affine> lp_, rp_;
+};
+
+}  // namespace b200zk

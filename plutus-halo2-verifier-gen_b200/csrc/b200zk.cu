@@ -111,7 +111,7 @@ struct Ctx {
     std::map<NttKey, NttPlan> ntt_plans;
     std::map<CosetKey, uint32_t*> coset_tables;
     uint32_t* fixed_table = nullptr;  // 8 x 256 multiples of G for the synthetic-base generator
-    uint32_t tune_c = 0, tune_smax = 0;
+    uint32_t tune_c = 0, tune_smax = 0, tune_variant = 0;
     // phase timing (b200zk_set_profiling): events recorded on the launching stream
     bool profiling = false;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -120,7 +120,7 @@ struct Ctx {
     MsmPlan last_plan{};
     // MSM workspace
     DevBuf scalars, counts, offsets, cursor, ntask, task_off, entries, task_bucket, task_start, task_len, buckets,
-        partials, redS[2], redA[2], scan_tmp[2], out_mont, out_canon, stage, flag;
+        partials, len_hist, len_off, order, heavy, redS[2], redA[2], scan_tmp[2], out_mont, out_canon, stage, flag;
     // NTT workspace
     DevBuf ntt_data, ntt_tmp[2], small;
 };
@@ -216,6 +216,10 @@ int32_t msm_run(const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, 
     TRY(g.task_bucket.ensure(max_tasks * 4));
     TRY(g.task_start.ensure(max_tasks * 4));
     TRY(g.task_len.ensure(max_tasks * 4));
+    TRY(g.len_hist.ensure(((size_t)pl.smax + 2) * 4));
+    TRY(g.len_off.ensure(((size_t)pl.smax + 2) * 4));
+    TRY(g.order.ensure(max_tasks * 4));
+    TRY(g.heavy.ensure((max_entries / pl.smax + 2) * 4));
     TRY(g.buckets.ensure(NBt * 192));
     TRY(g.partials.ensure(max_tasks * 192));
     uint64_t m1 = (pl.nb + RED_RADIX - 1) / RED_RADIX, m2 = (m1 + RED_RADIX - 1) / RED_RADIX;
@@ -247,17 +251,35 @@ int32_t msm_run(const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, 
     unsigned bgrid = (unsigned)((NBt + 255) / 256);
     LAUNCH(msm_task_count_kernel, bgrid, 256, 0, s, (const uint32_t*)counts, NBt, pl.smax, ntask);
     TRY(scan_u32(ntask, task_off, NBt + 1, 0, s));
+    uint32_t* len_hist = g.len_hist.as<uint32_t>();
+    uint32_t* len_off = g.len_off.as<uint32_t>();
+    uint32_t* order = g.order.as<uint32_t>();
+    uint32_t* heavy = g.heavy.as<uint32_t>();      // [0] = count, [1..] = bucket ids
+    CU(cudaMemsetAsync(len_hist, 0, ((size_t)pl.smax + 2) * 4, s));
+    CU(cudaMemsetAsync(heavy, 0, 4, s));
     LAUNCH(msm_task_emit_kernel, bgrid, 256, 0, s, (const uint32_t*)counts, (const uint32_t*)offsets,
            (const uint32_t*)task_off, NBt, pl.smax, g.task_bucket.as<uint32_t>(), g.task_start.as<uint32_t>(),
-           g.task_len.as<uint32_t>());
+           g.task_len.as<uint32_t>(), len_hist);
+    TRY(scan_u32(len_hist, len_off, (uint64_t)pl.smax + 1, 0, s));
+    LAUNCH(msm_task_order_kernel, (unsigned)((max_tasks + 255) / 256), 256, 0, s, (const uint32_t*)g.task_len.as<uint32_t>(),
+           (const uint32_t*)(task_off + NBt), pl.smax, len_off, order);
+    LAUNCH(msm_heavy_list_kernel, bgrid, 256, 0, s, (const uint32_t*)ntask, NBt, heavy, heavy + 1);
     CU(cudaMemsetAsync(buckets, 0, NBt * 192, s));
     TRY(prof_mark(1, s));
-    LAUNCH(msm_accumulate_kernel, (unsigned)((max_tasks + 127) / 128), 128, 0, s, d_bases, (const uint32_t*)entries,
-           (const uint32_t*)g.task_bucket.as<uint32_t>(), (const uint32_t*)g.task_start.as<uint32_t>(),
-           (const uint32_t*)g.task_len.as<uint32_t>(), (const uint32_t*)(task_off + NBt), buckets, partials);
+    {
+        unsigned agrid = (unsigned)((max_tasks + 127) / 128);
+        const uint32_t *tb = g.task_bucket.as<uint32_t>(), *ts = g.task_start.as<uint32_t>(), *tl = g.task_len.as<uint32_t>();
+        const uint32_t* ntp = task_off + NBt;
+        switch (g.tune_variant) {
+            case 1: LAUNCH(msm_accumulate_kernel_v1, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
+            case 2: LAUNCH(msm_accumulate_kernel_v2, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
+            case 3: LAUNCH(msm_accumulate_kernel_v3, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
+            default: LAUNCH(msm_accumulate_kernel, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
+        }
+    }
     TRY(prof_mark(2, s));
-    LAUNCH(msm_collapse_kernel, (unsigned)((NBt + 3) / 4), 128, 0, s, (const uint32_t*)ntask, (const uint32_t*)task_off,
-           NBt, (const uint32_t*)partials, buckets);
+    LAUNCH(msm_collapse_kernel, (unsigned)(g.prop.multiProcessorCount * 4), 128, 0, s, (const uint32_t*)ntask,
+           (const uint32_t*)task_off, (const uint32_t*)heavy, (const uint32_t*)(heavy + 1), (const uint32_t*)partials, buckets);
 
     // bucket reduction tree
     const uint32_t* S_in = buckets;
@@ -682,7 +704,7 @@ int32_t b200zk_shutdown(void) {
     g.coset_tables.clear();
     if (g.fixed_table) { cudaFree(g.fixed_table); g.fixed_table = nullptr; }
     DevBuf* all[] = {&g.scalars, &g.counts, &g.offsets, &g.cursor, &g.ntask, &g.task_off, &g.entries, &g.task_bucket,
-                     &g.task_start, &g.task_len, &g.buckets, &g.partials, &g.redS[0], &g.redS[1], &g.redA[0], &g.redA[1],
+                     &g.task_start, &g.task_len, &g.buckets, &g.partials, &g.len_hist, &g.len_off, &g.order, &g.heavy, &g.redS[0], &g.redS[1], &g.redA[0], &g.redA[1],
                      &g.scan_tmp[0], &g.scan_tmp[1], &g.out_mont, &g.out_canon, &g.stage, &g.flag, &g.ntt_data,
                      &g.ntt_tmp[0], &g.ntt_tmp[1], &g.small};
     for (DevBuf* b : all) b->release();
@@ -1033,7 +1055,8 @@ int32_t b200zk_get_profile(uint32_t* kind, double* phase_ms, uint32_t cap, uint3
 
 int32_t b200zk_set_msm_tuning(uint32_t window_bits, uint32_t smax) {
     std::lock_guard<std::mutex> lk(g_mu);
-    g.tune_c = window_bits;
+    g.tune_c = window_bits & 0xffu;
+    g.tune_variant = (window_bits >> 8) & 0xffu;   // bits 8..15: accumulate-kernel code variant (experiments)
     g.tune_smax = smax;
     return B200ZK_OK;
 }

@@ -197,9 +197,10 @@ __global__ void msm_task_count_kernel(const uint32_t* counts, uint64_t nbuckets,
     ntask[g] = (counts[g] + smax - 1) / smax;
 }
 // task t of bucket g covers entries [off[g] + k*smax, ...); bit 31 of task_len marks "bucket was split"
+// len_hist[smax - len] counts tasks by length, longest first, for the length sort below.
 __global__ void msm_task_emit_kernel(const uint32_t* counts, const uint32_t* offsets, const uint32_t* task_off,
                                      uint64_t nbuckets, uint32_t smax, uint32_t* task_bucket, uint32_t* task_start,
-                                     uint32_t* task_len) {
+                                     uint32_t* task_len, uint32_t* len_hist) {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nbuckets) return;
     uint32_t cnt = counts[g], off = offsets[g], t0 = task_off[g];
@@ -209,21 +210,72 @@ __global__ void msm_task_emit_kernel(const uint32_t* counts, const uint32_t* off
         task_bucket[t0 + k] = (uint32_t)g;
         task_start[t0 + k] = off + k * smax;
         task_len[t0 + k] = len | (nt > 1 ? 0x80000000u : 0u);
+        atomicAdd(&len_hist[smax - len], 1u);
     }
+}
+// order[pos] = task index, tasks grouped by length in descending order: the 32 lanes of a warp then
+// run loops of (almost) equal trip count, and the longest tasks start first
+__global__ void msm_task_order_kernel(const uint32_t* task_len, const uint32_t* ntasks_p, uint32_t smax,
+                                      uint32_t* len_cursor, uint32_t* order) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *ntasks_p) return;
+    uint32_t len = task_len[t] & 0x7fffffffu;
+    uint32_t pos = atomicAdd(&len_cursor[smax - len], 1u);
+    order[pos] = t;
 }
 
 // ---------------------------------------------------------------------------------------
-// 5. bucket accumulation: one thread per task
+// 5. bucket accumulation: one thread per task (tasks visited in length order)
+//    VARIANT selects the code shape, so that occupancy / code size trade-offs can be measured on
+//    the same build: 0 = Montgomery products inlined, registers unconstrained (2 CTAs of 128 per SM);
+//    1 = inlined, capped for 3 CTAs/SM; 2 = inlined, capped for 4 CTAs/SM;
+//    3 = products out of line (small loop body that stays in the instruction cache), 4 CTAs/SM.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __restrict__ bases,
-                                                             const uint32_t* __restrict__ entries,
-                                                             const uint32_t* __restrict__ task_bucket,
-                                                             const uint32_t* __restrict__ task_start,
-                                                             const uint32_t* __restrict__ task_len,
-                                                             const uint32_t* __restrict__ ntasks_p,
-                                                             uint32_t* __restrict__ buckets, uint32_t* __restrict__ partials) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= *ntasks_p) return;
+__device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) { return fe_mul(a, b); }
+struct MulInline {
+    static __device__ __forceinline__ Fp mul(const Fp& a, const Fp& b) { return fe_mul(a, b); }
+};
+struct MulCall {
+    static __device__ __forceinline__ Fp mul(const Fp& a, const Fp& b) { return fp_mul_call(a, b); }
+};
+// acc += (neg ? -q : q); same formulas as xyzz_add_mixed, ordered to keep few values live
+template <class M>
+__device__ __forceinline__ void xyzz_add_mixed_t(G1Xyzz& acc, const G1Affine& q, bool neg) {
+    if (g1a_is_inf(q)) return;
+    Fp qy = neg ? fe_neg(q.y) : q.y;
+    if (xyzz_is_inf(acc)) {
+        acc.x = q.x; acc.y = qy; acc.zz = fe_one<FpParams>(); acc.zzz = fe_one<FpParams>();
+        return;
+    }
+    Fp p = fe_sub(M::mul(q.x, acc.zz), acc.x);
+    Fp r = fe_sub(M::mul(qy, acc.zzz), acc.y);
+    if (fe_is_zero(p)) {
+        if (fe_is_zero(r)) xyzz_dbl_affine(acc, q.x, qy);
+        else xyzz_set_inf(acc);
+        return;
+    }
+    Fp pp = M::mul(p, p);
+    Fp qq = M::mul(acc.x, pp);
+    acc.zz = M::mul(acc.zz, pp);
+    Fp ppp = M::mul(p, pp);
+    acc.zzz = M::mul(acc.zzz, ppp);
+    Fp t = M::mul(acc.y, ppp);
+    Fp x3 = fe_sub(fe_sub(fe_sub(M::mul(r, r), ppp), qq), qq);
+    acc.y = fe_sub(M::mul(r, fe_sub(qq, x3)), t);
+    acc.x = x3;
+}
+
+template <int VARIANT>
+__device__ __forceinline__ void msm_accumulate_body(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ entries,
+                                                    const uint32_t* __restrict__ task_bucket,
+                                                    const uint32_t* __restrict__ task_start,
+                                                    const uint32_t* __restrict__ task_len,
+                                                    const uint32_t* __restrict__ order,
+                                                    const uint32_t* __restrict__ ntasks_p, uint32_t* __restrict__ buckets,
+                                                    uint32_t* __restrict__ partials) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *ntasks_p) return;
+    uint32_t t = order[i];
     uint32_t start = task_start[t], lenf = task_len[t];
     uint32_t len = lenf & 0x7fffffffu;
     G1Xyzz acc;
@@ -239,42 +291,62 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t* __r
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 64));
         }
         G1Affine pt = g1a_ldg(bases, cur & 0x7fffffffu);
-        xyzz_add_mixed(acc, pt, (cur >> 31) != 0);
+        if (VARIANT == 3) xyzz_add_mixed_t<MulCall>(acc, pt, (cur >> 31) != 0);
+        else xyzz_add_mixed_t<MulInline>(acc, pt, (cur >> 31) != 0);
     }
     if (lenf & 0x80000000u) xyzz_st(partials, t, acc);
     else xyzz_st(buckets, task_bucket[t], acc);
 }
+#define MSM_ACC_ARGS                                                                                              \
+    const uint32_t *__restrict__ bases, const uint32_t *__restrict__ entries, const uint32_t *__restrict__ task_bucket, \
+        const uint32_t *__restrict__ task_start, const uint32_t *__restrict__ task_len, const uint32_t *__restrict__ order, \
+        const uint32_t *__restrict__ ntasks_p, uint32_t *__restrict__ buckets, uint32_t *__restrict__ partials
+#define MSM_ACC_PASS bases, entries, task_bucket, task_start, task_len, order, ntasks_p, buckets, partials
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(MSM_ACC_ARGS) { msm_accumulate_body<0>(MSM_ACC_PASS); }
+__global__ void __launch_bounds__(128, 3) msm_accumulate_kernel_v1(MSM_ACC_ARGS) { msm_accumulate_body<1>(MSM_ACC_PASS); }
+__global__ void __launch_bounds__(128, 4) msm_accumulate_kernel_v2(MSM_ACC_ARGS) { msm_accumulate_body<2>(MSM_ACC_PASS); }
+__global__ void __launch_bounds__(128, 4) msm_accumulate_kernel_v3(MSM_ACC_ARGS) { msm_accumulate_body<3>(MSM_ACC_PASS); }
 
 // ---------------------------------------------------------------------------------------
-// 6. collapse split buckets: one warp per bucket, lanes stride over its task partials
+// 6. collapse split buckets: heavy_list holds the buckets that were split into several tasks
+//    (appended by msm_heavy_list_kernel); a fixed grid of warps walks the list, lanes stride over
+//    the bucket's task partials and a shared-memory tree folds the 32 lane sums.
 // ---------------------------------------------------------------------------------------
+__global__ void msm_heavy_list_kernel(const uint32_t* __restrict__ ntask, uint64_t nbuckets, uint32_t* heavy_count,
+                                      uint32_t* heavy_list) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nbuckets) return;
+    if (ntask[g] > 1) heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)g;
+}
 __global__ void __launch_bounds__(128) msm_collapse_kernel(const uint32_t* __restrict__ ntask, const uint32_t* __restrict__ task_off,
-                                                           uint64_t nbuckets, const uint32_t* __restrict__ partials,
+                                                           const uint32_t* __restrict__ heavy_count,
+                                                           const uint32_t* __restrict__ heavy_list,
+                                                           const uint32_t* __restrict__ partials,
                                                            uint32_t* __restrict__ buckets) {
     __shared__ uint32_t sm[4 * 16 * 48];  // per warp: 16 XYZZ points for the lane tree
-    uint64_t g = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (g >= nbuckets) return;
-    uint32_t nt = ntask[g];
-    if (nt <= 1) return;                      // whole warp leaves together
-    uint32_t t0 = task_off[g];
-    G1Xyzz acc;
-    xyzz_set_inf(acc);
-    for (uint32_t k = lane; k < nt; k += 32) {
-        G1Xyzz p = xyzz_ld(partials, t0 + k);
-        xyzz_add_ni(acc, p);
-    }
+    uint32_t nheavy = *heavy_count;
     uint32_t* my = sm + wid * 16 * 48;
-    for (int half = 16; half >= 1; half >>= 1) {
-        if (lane >= half && lane < 2 * half) xyzz_st(my, lane - half, acc);
-        __syncwarp();
-        if (lane < half) {
-            G1Xyzz p = xyzz_ld(my, lane);
+    for (uint32_t h = blockIdx.x * 4 + wid; h < nheavy; h += gridDim.x * 4) {
+        uint32_t g = heavy_list[h];
+        uint32_t nt = ntask[g], t0 = task_off[g];
+        G1Xyzz acc;
+        xyzz_set_inf(acc);
+        for (uint32_t k = lane; k < nt; k += 32) {
+            G1Xyzz p = xyzz_ld(partials, t0 + k);
             xyzz_add_ni(acc, p);
         }
-        __syncwarp();
+        for (int half = 16; half >= 1; half >>= 1) {
+            if (lane >= half && lane < 2 * half) xyzz_st(my, lane - half, acc);
+            __syncwarp();
+            if (lane < half) {
+                G1Xyzz p = xyzz_ld(my, lane);
+                xyzz_add_ni(acc, p);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) xyzz_st(buckets, g, acc);
     }
-    if (lane == 0) xyzz_st(buckets, g, acc);
 }
 
 // ---------------------------------------------------------------------------------------
