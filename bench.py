@@ -203,7 +203,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--window-bits", type=int, default=0)
-    ap.add_argument("--acc-variant", type=int, default=0, help="accumulate-kernel code variant (experiments)")
+    ap.add_argument("--acc-variant", type=int, default=-1, help="accumulate-kernel code variant (experiments)")
+    ap.add_argument("--no-tables", action="store_true", help="do not build window tables at registration")
     ap.add_argument("--smax", type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3:
@@ -227,8 +228,9 @@ def main():
     zdist = import_module("plutus-halo2-verifier-gen_b200.dist")
     zk.init(local_rank)
     lib = zk.lib()
-    if args.window_bits or args.acc_variant or args.smax:
-        lib.b200zk_set_msm_tuning(args.window_bits | (args.acc_variant << 8), args.smax)
+    if args.window_bits or args.acc_variant >= 0 or args.smax or args.no_tables:
+        lib.b200zk_set_msm_tuning(args.window_bits | ((args.acc_variant + 1) << 8 if args.acc_variant >= 0 else 0)
+                                  | (0x8000 if args.no_tables else 0), args.smax)
     stream = torch.cuda.current_stream().cuda_stream
 
     def barrier():

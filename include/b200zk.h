@@ -54,6 +54,11 @@ extern "C" {
 
 #define B200ZK_FMT_CANONICAL 0u
 #define B200ZK_FMT_MONT 1u
+/* OR-ed into the `fmt` of b200zk_bases_register*: keep only the points themselves.  By default a table of
+ * n >= 1024 points is expanded at registration into W rows 2^(c*w) * P_i (W = ceil(256/c) windows), which
+ * costs (W-1) * n * 96 bytes of HBM once and removes the per-window bucket sets and the window combine
+ * from every later MSM against it.                                                                     */
+#define B200ZK_BASES_NO_WINDOW_TABLES 0x100u
 
 /* NTT flags */
 #define B200ZK_NTT_INVERSE_SCALE 1u /* multiply the result by 1/n (caller passes omega^-1) */
@@ -152,7 +157,9 @@ uint64_t b200zk_launch_count(void);
 int32_t b200zk_set_profiling(uint32_t enable);
 int32_t b200zk_get_profile(uint32_t *kind, double *phase_ms, uint32_t cap, uint32_t *n_phases, uint32_t *msm_window_bits,
                            uint32_t *msm_windows);
-/* overrides for experiments: MSM window bits (0 = automatic) and max entries per task (0 = automatic) */
+/* overrides for experiments: window_bits bits 0..7 = MSM window bits (0 = automatic; also used for tables
+ * registered afterwards), bits 8..14 = 1 + accumulate-kernel code variant (0 = default), bit 15 = do not
+ * build window tables; smax = max entries per task (0 = automatic)                                      */
 int32_t b200zk_set_msm_tuning(uint32_t window_bits, uint32_t smax);
 
 #ifdef __cplusplus

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -72,8 +73,10 @@ struct DevBuf {
 };
 
 struct BaseTable {
-    uint32_t* d = nullptr;  // packed Montgomery affine, 24 limbs per point
+    uint32_t* d = nullptr;  // packed Montgomery affine, 24 limbs per point; `rows` rows of n points
     uint64_t n = 0;
+    uint32_t rows = 1;      // > 1: window tables, row w = 2^(c*w) * row 0
+    uint32_t c = 0;         // window bits the rows were built for
 };
 
 struct NttPlan {
@@ -111,7 +114,7 @@ struct Ctx {
     std::map<NttKey, NttPlan> ntt_plans;
     std::map<CosetKey, uint32_t*> coset_tables;
     uint32_t* fixed_table = nullptr;  // 8 x 256 multiples of G for the synthetic-base generator
-    uint32_t tune_c = 0, tune_smax = 0, tune_variant = 0;
+    uint32_t tune_c = 0, tune_smax = 0, tune_variant = 3, tune_no_tables = 0;
     // phase timing (b200zk_set_profiling): events recorded on the launching stream
     bool profiling = false;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -162,48 +165,60 @@ int32_t scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, int level, cudaS
 // ------------------------------------------------------------------------------------------
 // MSM
 // ------------------------------------------------------------------------------------------
-MsmPlan msm_plan(uint64_t n, uint32_t batch) {
-    MsmPlan best{};
+// window bits minimising (mixed adds) + (bucket reduction); `shared` = all windows share one bucket set
+uint32_t msm_choose_window(uint64_t n, uint32_t batch, bool shared) {
+    uint32_t best_c = 4;
     double best_cost = 1e300;
-    for (uint32_t c = 4; c <= 22; c++) {
+    for (uint32_t c = 4; c <= 24; c++) {
         uint32_t W = (256 + c - 1) / c;
         double nb = (double)(1u << (c - 1));
+        double sets = shared ? 1.0 : (double)W;
         // mixed add ~10 Fp mul per point and window; bucket reduce ~2.2 full adds (14 mul) per bucket
-        double cost = W * (10.0 * (double)n + 31.0 * nb);
-        // keep the bucket arrays within ~4 GiB
-        if ((double)batch * W * nb * 192.0 > 4.0e9 && c > 8) continue;
-        if (cost < best_cost) { best_cost = cost; best.c = c; best.W = W; best.nb = 1u << (c - 1); }
+        double cost = W * 10.0 * (double)n + sets * 31.0 * nb;
+        if ((double)batch * sets * nb * 192.0 > 4.0e9 && c > 8) continue;   // bucket arrays within ~4 GB
+        if (cost < best_cost) { best_cost = cost; best_c = c; }
     }
-    if (g.tune_c >= 2 && g.tune_c <= 24) {
-        best.c = g.tune_c;
-        best.W = (256 + best.c - 1) / best.c;
-        best.nb = 1u << (best.c - 1);
+    return best_c;
+}
+
+MsmPlan msm_plan(uint64_t n, uint32_t batch, const BaseTable* tab) {
+    MsmPlan pl{};
+    bool precomp = tab && tab->rows > 1 && n * 16 >= tab->n;   // tiny slices of a big table: plain path
+    if (precomp) {
+        pl.c = tab->c;
+        pl.precomp = 1;
+        pl.row_stride = tab->n;
+    } else {
+        pl.c = msm_choose_window(n, batch, false);
+        if (g.tune_c >= 2 && g.tune_c <= 24) pl.c = g.tune_c;
     }
-    double avg = (double)n / (double)best.nb;
+    pl.W = (256 + pl.c - 1) / pl.c;
+    pl.nb = 1u << (pl.c - 1);
+    double avg = (double)n * (precomp ? pl.W : 1) / (double)pl.nb;
     uint32_t smax = 32;
     while ((double)smax < 2.0 * avg && smax < (1u << 20)) smax <<= 1;
     // small problems: split further so that the accumulate kernel still fills the machine
-    double entries = (double)n * best.W * batch;
+    double entries = (double)n * pl.W * batch;
     while (smax > 8 && entries / smax < 131072.0) smax >>= 1;
     if (g.tune_smax) smax = g.tune_smax;
-    best.smax = smax;
-    return best;
+    pl.smax = smax;
+    return pl;
 }
 
 // d_scalars: batch*n Fr (device).  d_bases: n packed Montgomery affine points.
-int32_t msm_run(const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, uint32_t batch, uint32_t scalar_fmt,
-                uint32_t* d_out_mont, uint32_t* d_out_canon, cudaStream_t s) {
+int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, uint32_t batch,
+                uint32_t scalar_fmt, uint32_t* d_out_mont, uint32_t* d_out_canon, cudaStream_t s) {
     if (n == 0 || batch == 0) {
         if (d_out_mont) CU(cudaMemsetAsync(d_out_mont, 0, 96 * (size_t)std::max(batch, 1u), s));
         if (d_out_canon) CU(cudaMemsetAsync(d_out_canon, 0, 96 * (size_t)std::max(batch, 1u), s));
         return B200ZK_OK;
     }
     if (n >= (1ull << 31)) return fail(B200ZK_ERR_INVALID_ARG, "msm: n must be < 2^31");
-    MsmPlan pl = msm_plan(n, batch);
-    uint64_t nwin = (uint64_t)batch * pl.W;
+    MsmPlan pl = msm_plan(n, batch, tab);
+    uint64_t nwin = (uint64_t)batch * (pl.precomp ? 1 : pl.W);   // bucket sets
     uint64_t NBt = nwin * pl.nb;
     uint64_t max_entries = (uint64_t)batch * n * pl.W;
-    if (max_entries >= (1ull << 32) || NBt >= (1ull << 31))
+    if (max_entries >= (1ull << 32) || NBt >= (1ull << 31) || (pl.precomp && pl.row_stride * pl.W >= (1ull << 31)))
         return fail(B200ZK_ERR_INVALID_ARG, "msm: batch * n * windows exceeds 2^32 entries; split the batch");
     uint64_t max_tasks = std::min(NBt, max_entries) + max_entries / pl.smax + 1;
 
@@ -301,18 +316,19 @@ int32_t msm_run(const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, 
         scale_log += RED_LOG;
         pp ^= 1;
     } while (m > 1);
-    LAUNCH(msm_combine_kernel, batch, 32, 0, s, win_sums, pl.W, pl.c, d_out_mont, d_out_canon);
+    LAUNCH(msm_combine_kernel, batch, 32, 0, s, win_sums, pl.precomp ? 1u : pl.W, pl.c, d_out_mont, d_out_canon);
     TRY(prof_mark(3, s));
     g.last_plan = pl;
     return B200ZK_OK;
 }
 
-int32_t lookup_bases(uint64_t handle, uint64_t offset, uint64_t n, const uint32_t** out) {
+int32_t lookup_bases(uint64_t handle, uint64_t offset, uint64_t n, const uint32_t** out, const BaseTable** tab = nullptr) {
     auto it = g.tables.find(handle);
     if (it == g.tables.end()) return fail(B200ZK_ERR_BAD_HANDLE, "unknown base-table handle");
     if (offset > it->second.n || n > it->second.n - offset)
         return fail(B200ZK_ERR_INVALID_ARG, "msm: offset + n exceeds the registered table");
     *out = it->second.d + 24 * offset;
+    if (tab) *tab = &it->second;
     return B200ZK_OK;
 }
 
@@ -424,8 +440,11 @@ int32_t ntt_run(uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t 
         }
     }
     static bool attr_set = false;
+    static int ntt_variant = 1;   // 1: two CTAs per SM (default); 0: one CTA per SM.  B200ZK_NTT_VARIANT overrides.
     if (!attr_set) {
         CU(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+        CU(cudaFuncSetAttribute(ntt_pass_kernel_occ2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+        if (const char* v = getenv("B200ZK_NTT_VARIANT")) ntt_variant = atoi(v);
         attr_set = true;
     }
     uint32_t log_s = 0;
@@ -452,7 +471,8 @@ int32_t ntt_run(uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t 
         a.log_cols = log_n - pl->deg[i];
         a.total_cols = (uint64_t)batch << a.log_cols;
         uint64_t ctas = (total + NTT_B - 1) / NTT_B;
-        LAUNCH(ntt_pass_kernel, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+        if (ntt_variant == 0) LAUNCH(ntt_pass_kernel, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+        else LAUNCH(ntt_pass_kernel_occ2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         TRY(prof_mark((int)i + 1, s));
         src = dst;
         log_s += pl->deg[i];
@@ -742,12 +762,33 @@ int32_t b200zk_host_free(void* p) {
     return B200ZK_OK;
 }
 
-static int32_t register_common(const uint8_t* d_src, uint64_t n, uint32_t fmt, uint32_t stride, uint64_t* out_handle) {
+static int32_t register_common(const uint8_t* d_src, uint64_t n, uint32_t fmt_flags, uint32_t stride, uint64_t* out_handle) {
     BaseTable t;
     t.n = n;
-    CU(cudaMalloc(&t.d, std::max<uint64_t>(n, 1) * 96));
+    uint32_t fmt = fmt_flags & 0xffu;
+    // Window tables: W rows of n points.  Built for resident SRS tables (they are registered once and
+    // committed against many times); skipped on request, for tiny tables, or when HBM is short.
+    bool want_rows = !(fmt_flags & B200ZK_BASES_NO_WINDOW_TABLES) && !g.tune_no_tables && n >= 1024;
+    uint32_t c = 0, W = 1;
+    if (want_rows) {
+        c = (g.tune_c >= 2 && g.tune_c <= 24) ? g.tune_c : msm_choose_window(n, 1, true);
+        W = (256 + c - 1) / c;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if ((double)W * n * 96.0 > 0.45 * (double)free_b || (double)W * n >= 2147483648.0 || W > (uint32_t)MSM_MAX_ROWS) { W = 1; c = 0; }
+    }
+    CU(cudaMalloc(&t.d, std::max<uint64_t>(n, 1) * 96 * W));
     int32_t rc = n ? ingest_bases(d_src, n, fmt, stride, t.d, g.stream) : B200ZK_OK;
     if (rc != B200ZK_OK) { cudaFree(t.d); return rc; }
+    if (W > 1) {
+        g1_window_tables_kernel<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(t.d, n, c, W);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+        if (e != cudaSuccess) { cudaFree(t.d); return fail(B200ZK_ERR_CUDA, std::string("window tables: ") + cudaGetErrorString(e)); }
+        t.rows = W;
+        t.c = c;
+    }
     uint64_t h = g.next_handle++;
     g.tables[h] = t;
     *out_handle = h;
@@ -759,7 +800,7 @@ int32_t b200zk_bases_register(const uint8_t* g1_affine, uint64_t n, uint32_t fmt
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(need_init());
     if (!out_handle || (!g1_affine && n)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
-    if (fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown point format");
+    if ((fmt & 0xffu) > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown point format");
     uint32_t stride = stride_bytes ? stride_bytes : 96;
     if (stride < 96 || (stride & 3)) return fail(B200ZK_ERR_INVALID_ARG, "stride must be >= 96 and a multiple of 4");
     size_t bytes = n ? (size_t)(n - 1) * stride + 96 : 0;
@@ -773,7 +814,7 @@ int32_t b200zk_bases_register_dev(const void* d_g1_affine, uint64_t n, uint32_t 
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(need_init());
     if (!out_handle || (!d_g1_affine && n)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
-    if (fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown point format");
+    if ((fmt & 0xffu) > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown point format");
     uint32_t stride = stride_bytes ? stride_bytes : 96;
     if (stride < 96 || (stride & 3)) return fail(B200ZK_ERR_INVALID_ARG, "stride must be >= 96 and a multiple of 4");
     CU(cudaDeviceSynchronize());  // the source may have been produced on another stream
@@ -813,12 +854,13 @@ int32_t b200zk_msm_g1_batch(uint64_t bases, uint64_t offset, const uint8_t* scal
     if (scalar_fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown scalar format");
     if (batch == 0) return B200ZK_OK;
     const uint32_t* d_bases = nullptr;
-    TRY(lookup_bases(bases, offset, n, &d_bases));
+    const BaseTable* tab = nullptr;
+    TRY(lookup_bases(bases, offset, n, &d_bases, &tab));
     size_t bytes = (size_t)n * batch * 32;
     TRY(g.scalars.ensure(bytes + 16));
     TRY(g.out_canon.ensure((size_t)batch * 96));
     if (bytes) CU(cudaMemcpyAsync(g.scalars.p, scalars, bytes, cudaMemcpyHostToDevice, g.stream));
-    TRY(msm_run(d_bases, g.scalars.as<uint32_t>(), n, batch, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream));
+    TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>(), n, batch, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream));
     CU(cudaMemcpyAsync(out_affine, g.out_canon.p, (size_t)batch * 96, cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
     return B200ZK_OK;
@@ -832,7 +874,7 @@ int32_t b200zk_msm_g1(uint64_t bases, uint64_t offset, const uint8_t* scalars, u
 int32_t b200zk_msm_g1_adhoc(const uint8_t* g1_affine, uint32_t point_fmt, const uint8_t* scalars, uint32_t scalar_fmt,
                             uint64_t n, uint8_t out_affine[96]) {
     uint64_t h = 0;
-    int32_t rc = b200zk_bases_register(g1_affine, n, point_fmt, 96, &h);
+    int32_t rc = b200zk_bases_register(g1_affine, n, point_fmt | B200ZK_BASES_NO_WINDOW_TABLES, 96, &h);
     if (rc != B200ZK_OK) return rc;
     rc = b200zk_msm_g1(h, 0, scalars, n, scalar_fmt, out_affine);
     std::string keep = t_err;
@@ -850,8 +892,9 @@ int32_t b200zk_msm_g1_dev(uint64_t bases, uint64_t offset, const void* d_scalars
     if (((uintptr_t)d_scalars | (uintptr_t)d_out_mont | (uintptr_t)d_out_canon) & 15)
         return fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
     const uint32_t* d_bases = nullptr;
-    TRY(lookup_bases(bases, offset, n, &d_bases));
-    return msm_run(d_bases, reinterpret_cast<const uint32_t*>(d_scalars), n, batch, scalar_fmt,
+    const BaseTable* tab = nullptr;
+    TRY(lookup_bases(bases, offset, n, &d_bases, &tab));
+    return msm_run(tab, d_bases, reinterpret_cast<const uint32_t*>(d_scalars), n, batch, scalar_fmt,
                    reinterpret_cast<uint32_t*>(d_out_mont), reinterpret_cast<uint32_t*>(d_out_canon),
                    reinterpret_cast<cudaStream_t>(stream));
 }
@@ -1056,7 +1099,8 @@ int32_t b200zk_get_profile(uint32_t* kind, double* phase_ms, uint32_t cap, uint3
 int32_t b200zk_set_msm_tuning(uint32_t window_bits, uint32_t smax) {
     std::lock_guard<std::mutex> lk(g_mu);
     g.tune_c = window_bits & 0xffu;
-    g.tune_variant = (window_bits >> 8) & 0xffu;   // bits 8..15: accumulate-kernel code variant (experiments)
+    g.tune_variant = ((window_bits >> 8) & 0x7fu) ? ((window_bits >> 8) & 0x7fu) - 1 : 3;  // bits 8..14: 1 + accumulate-kernel variant
+    g.tune_no_tables = (window_bits >> 15) & 1u;    // bit 15: do not build window tables at registration
     g.tune_smax = smax;
     return B200ZK_OK;
 }

@@ -27,6 +27,8 @@ struct MsmPlan {
     uint32_t W;      // windows = ceil(256 / c)
     uint32_t nb;     // buckets per window = 2^(c-1)
     uint32_t smax;   // max entries per task
+    uint32_t precomp;      // 1: bases hold W rows T_w[i] = 2^(c*w) * P_i, all windows share one bucket set
+    uint64_t row_stride;   // points per table row (precomp only)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -139,11 +141,13 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint32_t* __restr
         int32_t d = msm_digit(s, w, pl.c, carry);
         if (d == 0) continue;
         uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-        uint32_t g = (b * pl.W + w) * pl.nb + mag - 1;
+        // with precomputed rows every window feeds the same bucket set and the entry names the row
+        uint32_t g = pl.precomp ? b * pl.nb + mag - 1 : (b * pl.W + w) * pl.nb + mag - 1;
         if (MODE == 0) atomicAdd(&counts_or_cursor[g], 1u);
         else {
             uint32_t pos = atomicAdd(&counts_or_cursor[g], 1u);
-            entries[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+            uint32_t idx = pl.precomp ? (uint32_t)(w * pl.row_stride + i) : (uint32_t)i;
+            entries[pos] = idx | (d < 0 ? 0x80000000u : 0u);
         }
     }
 }
@@ -445,6 +449,46 @@ __global__ void g1_export_kernel(const uint32_t* __restrict__ src, uint64_t n, u
     if (i >= n) return;
     fp_st(dst + 24 * i, fe_from_mont(fp_ld(src + 24 * i)));
     fp_st(dst + 24 * i + 12, fe_from_mont(fp_ld(src + 24 * i + 12)));
+}
+
+// ---------------------------------------------------------------------------------------
+// window tables: rows[w*n + i] = 2^(c*w) * P_i for w = 1..W-1 (row 0 is the ingested table).
+// With them the W windows of a scalar become W independent (row, digit) terms over ONE bucket
+// set: no Horner pass over windows, W-times fewer buckets to reduce, and room for a wider window.
+// One thread per point: c doublings per row in XYZZ, then a single inversion shared by the
+// point's W-1 rows (Montgomery's trick over the in-thread prefix products).
+// ---------------------------------------------------------------------------------------
+constexpr int MSM_MAX_ROWS = 32;   // c >= 8
+__global__ void __launch_bounds__(128) g1_window_tables_kernel(uint32_t* __restrict__ rows, uint64_t n, uint32_t c, uint32_t W) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p0 = g1a_ldg(rows, i);
+    if (g1a_is_inf(p0)) {
+        for (uint32_t w = 1; w < W; w++) { fp_st(rows + 24 * (w * n + i), p0.x); fp_st(rows + 24 * (w * n + i) + 12, p0.y); }
+        return;
+    }
+    Fp zz[MSM_MAX_ROWS], zzz[MSM_MAX_ROWS], pre[MSM_MAX_ROWS];   // local memory; this kernel runs once per table
+    G1Xyzz cur;
+    xyzz_from_affine(cur, p0, false);
+    Fp run = fe_one<FpParams>();
+    for (uint32_t w = 1; w < W; w++) {
+        for (uint32_t k = 0; k < c; k++) xyzz_dbl_ni(cur);
+        // X, Y parked in the output slot until the shared inverse is known
+        fp_st(rows + 24 * (w * n + i), cur.x);
+        fp_st(rows + 24 * (w * n + i) + 12, cur.y);
+        zz[w] = cur.zz;
+        zzz[w] = cur.zzz;
+        pre[w] = run;                                     // product of the denominators of rows < w
+        run = fp_mul_ni(run, fp_mul_ni(cur.zz, cur.zzz));
+    }
+    Fp inv = fp_inv_ni(run);
+    for (uint32_t w = W - 1; w >= 1; w--) {
+        Fp t = fp_mul_ni(inv, pre[w]);                    // 1 / (zz_w * zzz_w)
+        inv = fp_mul_ni(inv, fp_mul_ni(zz[w], zzz[w]));
+        Fp x = fp_ld(rows + 24 * (w * n + i)), y = fp_ld(rows + 24 * (w * n + i) + 12);
+        fp_st(rows + 24 * (w * n + i), fp_mul_ni(x, fp_mul_ni(t, zzz[w])));
+        fp_st(rows + 24 * (w * n + i) + 12, fp_mul_ni(y, fp_mul_ni(t, zz[w])));
+    }
 }
 
 // ---------------------------------------------------------------------------------------

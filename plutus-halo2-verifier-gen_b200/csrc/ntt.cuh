@@ -120,7 +120,7 @@ __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restri
     for (int j = 0; j < 8; j++) ntt_sts(sm, base | ((uint32_t)j << lb), v[j]);
 }
 
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) {
+__device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     extern __shared__ uint32_t sm[];
     const uint32_t tid = threadIdx.x;
     const uint32_t deg = a.deg;
@@ -182,6 +182,10 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) {
         ntt_st(a.out + 8 * ((poly << a.log_n) + oi), v);
     }
 }
+
+// one CTA per SM (registers unconstrained) and two CTAs per SM (<= 128 registers); the plan picks
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) { ntt_pass_body(a); }
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_occ2(NttPassArgs a) { ntt_pass_body(a); }
 
 // out[i] = scale * base^(e0 + i*mult mod 2^64), generic table generator (Montgomery form in and out).
 // kind 0: exponent = i * mult.  kind 1 (pass table): i = p*R + k, exponent = mult * p * k.

@@ -17,6 +17,9 @@ def fr(x):
     return (x % R).to_bytes(32, "little")
 
 
+NO_TABLES = 0x100   # B200ZK_BASES_NO_WINDOW_TABLES
+
+
 def register(gpu, pts: bytes, n, fmt=0, stride=0):
     h = C.c_uint64(0)
     gpu.capi.check(gpu.lib().b200zk_bases_register(gpu.capi.addr(pts), n, fmt, stride, C.byref(h)))
@@ -126,14 +129,25 @@ def test_prover_like_skew(gpu, oracle, table):
 
 
 @pytest.mark.parametrize("c,smax", [(4, 8), (7, 16), (10, 0), (13, 8), (16, 0), (18, 64)])
-def test_all_window_sizes_and_task_splits(gpu, oracle, table, c, smax):
-    pts, h, _ = table
+@pytest.mark.parametrize("tables", [False, True])
+def test_all_window_sizes_and_task_splits(gpu, oracle, table, c, smax, tables):
+    """every window width, with and without the precomputed window tables, forced task splits,
+    and every accumulate-kernel code variant"""
+    pts, _, _ = table
     n = 3000
     sc = oracle.synth_scalars(10 + c, 0, n)
     exp = oracle.msm(pts, sc, n)
     try:
+        if tables and c < 8:
+            pytest.skip("window tables need c >= 8")
         gpu.capi.check(gpu.lib().b200zk_set_msm_tuning(c, smax))
+        h = register(gpu, pts, n, fmt=0 if tables else NO_TABLES)
         assert msm(gpu, h, sc, n) == exp
+        assert msm(gpu, h, sc[32 * 100:], n - 500, offset=100) == oracle.msm(pts[96 * 100:], sc[32 * 100:], n - 500)
+        for variant in range(4):
+            gpu.capi.check(gpu.lib().b200zk_set_msm_tuning(c | ((variant + 1) << 8), smax))
+            assert msm(gpu, h, sc, n) == exp, variant
+        gpu.capi.check(gpu.lib().b200zk_bases_release(h))
     finally:
         gpu.lib().b200zk_set_msm_tuning(0, 0)
 
