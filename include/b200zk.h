@@ -113,6 +113,14 @@ int32_t b200zk_msm_g1_adhoc(const uint8_t *g1_affine, uint32_t point_fmt, const 
  * to d_out_mont and/or (canonical) to d_out_canon; asynchronous on `stream`.                  */
 int32_t b200zk_msm_g1_dev(uint64_t bases, uint64_t offset, const void *d_scalars, uint64_t n, uint32_t batch,
                           uint32_t scalar_fmt, void *d_out_mont, void *d_out_canon, void *stream);
+/* Point-range sharded MSM (one process per GPU): each rank computes the sum over its slice of the table
+ * and leaves it un-normalised (extended Jacobian X,Y,ZZ,ZZZ in Montgomery form, 192 bytes) in HBM; the
+ * ranks all-gather the 192-byte partials over NVLink and every rank folds them with one call.  Skipping
+ * the per-rank affine normalisation takes one field inversion off the critical path.                    */
+int32_t b200zk_msm_g1_partial_dev(uint64_t bases, uint64_t offset, const void *d_scalars, uint64_t n, uint32_t scalar_fmt,
+                                  void *d_out_xyzz, void *stream);
+int32_t b200zk_g1_sum_partials_dev(const void *d_partials_xyzz, uint32_t n, void *d_out_mont, void *d_out_canon,
+                                   void *stream);
 /* Sum of n affine points: combines the per-GPU partial results of a point-range sharded MSM
  * (Montgomery affine in HBM, e.g. the all-gathered d_out_mont of every rank).                */
 int32_t b200zk_g1_sum_dev(const void *d_points_mont, uint32_t n, void *d_out_mont, void *d_out_canon, void *stream);

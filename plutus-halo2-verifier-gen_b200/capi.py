@@ -54,6 +54,8 @@ SIGNATURES = {
     "b200zk_msm_g1_adhoc": (C.c_int32, [_u8p, C.c_uint32, _u8p, C.c_uint32, C.c_uint64, _u8p]),
     "b200zk_msm_g1_dev": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200zk_msm_g1_partial_dev": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "b200zk_g1_sum_partials_dev": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200zk_g1_sum_dev": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200zk_ntt_fr": (C.c_int32, [_u8p, C.c_uint32, _u8p, C.c_uint32, _u8p]),
     "b200zk_ntt_fr_batch": (C.c_int32, [_u8p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, _u8p]),

@@ -207,7 +207,8 @@ MsmPlan msm_plan(uint64_t n, uint32_t batch, const BaseTable* tab) {
 
 // d_scalars: batch*n Fr (device).  d_bases: n packed Montgomery affine points.
 int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, uint32_t batch,
-                uint32_t scalar_fmt, uint32_t* d_out_mont, uint32_t* d_out_canon, cudaStream_t s) {
+                uint32_t scalar_fmt, uint32_t* d_out_mont, uint32_t* d_out_canon, cudaStream_t s,
+                uint32_t* d_out_xyzz = nullptr) {
     if (n == 0 || batch == 0) {
         if (d_out_mont) CU(cudaMemsetAsync(d_out_mont, 0, 96 * (size_t)std::max(batch, 1u), s));
         if (d_out_canon) CU(cudaMemsetAsync(d_out_canon, 0, 96 * (size_t)std::max(batch, 1u), s));
@@ -296,27 +297,34 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     LAUNCH(msm_collapse_kernel, (unsigned)(g.prop.multiProcessorCount * 4), 128, 0, s, (const uint32_t*)ntask,
            (const uint32_t*)task_off, (const uint32_t*)heavy, (const uint32_t*)(heavy + 1), (const uint32_t*)partials, buckets);
 
-    // bucket reduction tree
+    // bucket reduction tree: work-efficient serial radix-16 groups while there are enough of them to fill
+    // the machine, then warp-cooperative radix-32 groups (short dependency chains) for the upper levels
     const uint32_t* S_in = buckets;
     const uint32_t* A_in = nullptr;
     uint32_t m = pl.nb, scale_log = 0;
     int pp = 0;
     const uint32_t* win_sums = nullptr;
     do {
-        uint32_t m_out = (m + RED_RADIX - 1) / RED_RADIX;
+        bool serial = (uint64_t)((m + RED_RADIX - 1) / RED_RADIX) * nwin >= 32768;
+        uint32_t radix = serial ? RED_RADIX : COOP_RADIX;
+        uint32_t m_out = (m + radix - 1) / radix;
         uint32_t* S_out = g.redS[pp].as<uint32_t>();
         uint32_t* A_out = g.redA[pp].as<uint32_t>();
-        uint64_t threads = (uint64_t)m_out * nwin;
-        LAUNCH(msm_reduce_kernel, (unsigned)((threads + 63) / 64), 64, 0, s, S_in, A_in, S_out, A_out, m, m_out,
-               (uint32_t)nwin, scale_log);
+        uint64_t groups = (uint64_t)m_out * nwin;
+        if (serial)
+            LAUNCH(msm_reduce_kernel, (unsigned)((groups + 63) / 64), 64, 0, s, S_in, A_in, S_out, A_out, m, m_out,
+                   (uint32_t)nwin, scale_log);
+        else
+            LAUNCH(msm_reduce_coop_kernel, (unsigned)((groups + 3) / 4), 128, 0, s, S_in, A_in, S_out, A_out, m, m_out,
+                   (uint32_t)nwin, scale_log);
         S_in = S_out;
         A_in = A_out;
         win_sums = A_out;
         m = m_out;
-        scale_log += RED_LOG;
+        scale_log += serial ? RED_LOG : COOP_LOG;
         pp ^= 1;
     } while (m > 1);
-    LAUNCH(msm_combine_kernel, batch, 32, 0, s, win_sums, pl.precomp ? 1u : pl.W, pl.c, d_out_mont, d_out_canon);
+    LAUNCH(msm_combine_kernel, batch, 32, 0, s, win_sums, pl.precomp ? 1u : pl.W, pl.c, d_out_mont, d_out_canon, d_out_xyzz);
     TRY(prof_mark(3, s));
     g.last_plan = pl;
     return B200ZK_OK;
@@ -897,6 +905,30 @@ int32_t b200zk_msm_g1_dev(uint64_t bases, uint64_t offset, const void* d_scalars
     return msm_run(tab, d_bases, reinterpret_cast<const uint32_t*>(d_scalars), n, batch, scalar_fmt,
                    reinterpret_cast<uint32_t*>(d_out_mont), reinterpret_cast<uint32_t*>(d_out_canon),
                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t b200zk_msm_g1_partial_dev(uint64_t bases, uint64_t offset, const void* d_scalars, uint64_t n, uint32_t scalar_fmt,
+                                  void* d_out_xyzz, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(need_init());
+    if ((!d_scalars && n) || !d_out_xyzz) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    if (scalar_fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown scalar format");
+    if (((uintptr_t)d_scalars | (uintptr_t)d_out_xyzz) & 15) return fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
+    const uint32_t* d_bases = nullptr;
+    const BaseTable* tab = nullptr;
+    TRY(lookup_bases(bases, offset, n, &d_bases, &tab));
+    if (n == 0) { CU(cudaMemsetAsync(d_out_xyzz, 0, 192, reinterpret_cast<cudaStream_t>(stream))); return B200ZK_OK; }
+    return msm_run(tab, d_bases, reinterpret_cast<const uint32_t*>(d_scalars), n, 1, scalar_fmt, nullptr, nullptr,
+                   reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<uint32_t*>(d_out_xyzz));
+}
+
+int32_t b200zk_g1_sum_partials_dev(const void* d_partials_xyzz, uint32_t n, void* d_out_mont, void* d_out_canon, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(need_init());
+    if ((!d_partials_xyzz && n) || (!d_out_mont && !d_out_canon)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    LAUNCH(g1_sum_xyzz_kernel, 1, 32, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const uint32_t*>(d_partials_xyzz),
+           n, reinterpret_cast<uint32_t*>(d_out_mont), reinterpret_cast<uint32_t*>(d_out_canon));
+    return B200ZK_OK;
 }
 
 int32_t b200zk_g1_sum_dev(const void* d_points_mont, uint32_t n, void* d_out_mont, void* d_out_canon, void* stream) {

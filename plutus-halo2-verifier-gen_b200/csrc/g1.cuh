@@ -22,6 +22,12 @@ struct G1Xyzz {
     Fp x, y, zz, zzz;
 };
 
+// how the point formulas obtain their field products: inlined (hot kernels tune this) or, in
+// msm.cuh, an out-of-line call that keeps the code small
+struct MulInline {
+    static HD Fp mul(const Fp& a, const Fp& b) { return fe_mul(a, b); }
+};
+
 HD bool g1a_is_inf(const G1Affine& a) { return fe_is_zero(a.x) && fe_is_zero(a.y); }
 HD bool xyzz_is_inf(const G1Xyzz& a) { return fe_is_zero(a.zz); }
 HD void xyzz_set_inf(G1Xyzz& a) {
@@ -52,20 +58,21 @@ HD void xyzz_dbl_affine(G1Xyzz& r, const Fp& qx, const Fp& qy) {
 }
 
 // acc = 2*acc (EFD dbl-2008-s-1, a = 0)
-HD void xyzz_dbl(G1Xyzz& a) {
+template <class M> HD void xyzz_dbl_t(G1Xyzz& a) {
     if (xyzz_is_inf(a)) return;
     Fp u = fe_dbl(a.y);
-    Fp v = fe_sqr(u);
-    Fp w = fe_mul(u, v);
-    Fp s = fe_mul(a.x, v);
-    Fp m = fe_sqr(a.x);
+    Fp v = M::mul(u, u);
+    Fp w = M::mul(u, v);
+    Fp s = M::mul(a.x, v);
+    Fp m = M::mul(a.x, a.x);
     m = fe_add(fe_dbl(m), m);
-    Fp x3 = fe_sub(fe_sub(fe_sqr(m), s), s);
-    Fp y3 = fe_sub(fe_mul(m, fe_sub(s, x3)), fe_mul(w, a.y));
-    a.zz = fe_mul(v, a.zz);
-    a.zzz = fe_mul(w, a.zzz);
+    Fp x3 = fe_sub(fe_sub(M::mul(m, m), s), s);
+    Fp y3 = fe_sub(M::mul(m, fe_sub(s, x3)), M::mul(w, a.y));
+    a.zz = M::mul(v, a.zz);
+    a.zzz = M::mul(w, a.zzz);
     a.x = x3; a.y = y3;
 }
+HD void xyzz_dbl(G1Xyzz& a) { xyzz_dbl_t<MulInline>(a); }
 
 // acc += (neg ? -q : q), q affine (EFD madd-2008-s: 8M + 2S)
 HD void xyzz_add_mixed(G1Xyzz& acc, const G1Affine& q, bool neg) {
@@ -95,35 +102,36 @@ HD void xyzz_add_mixed(G1Xyzz& acc, const G1Affine& q, bool neg) {
 }
 
 // acc += q, both XYZZ (EFD add-2008-s: 12M + 2S)
-HD void xyzz_add(G1Xyzz& acc, const G1Xyzz& q) {
+template <class M> HD void xyzz_add_t(G1Xyzz& acc, const G1Xyzz& q) {
     if (xyzz_is_inf(q)) return;
     if (xyzz_is_inf(acc)) { acc = q; return; }
-    Fp u1 = fe_mul(acc.x, q.zz);
-    Fp u2 = fe_mul(q.x, acc.zz);
-    Fp s1 = fe_mul(acc.y, q.zzz);
-    Fp s2 = fe_mul(q.y, acc.zzz);
+    Fp u1 = M::mul(acc.x, q.zz);
+    Fp u2 = M::mul(q.x, acc.zz);
+    Fp s1 = M::mul(acc.y, q.zzz);
+    Fp s2 = M::mul(q.y, acc.zzz);
     Fp p = fe_sub(u2, u1);
     Fp r = fe_sub(s2, s1);
     if (fe_is_zero(p)) {
-        if (fe_is_zero(r)) xyzz_dbl(acc);
+        if (fe_is_zero(r)) xyzz_dbl_t<M>(acc);
         else xyzz_set_inf(acc);
         return;
     }
-    Fp pp = fe_sqr(p);
-    Fp ppp = fe_mul(p, pp);
-    Fp qq = fe_mul(u1, pp);
-    Fp x3 = fe_sub(fe_sub(fe_sub(fe_sqr(r), ppp), qq), qq);
-    Fp y3 = fe_sub(fe_mul(r, fe_sub(qq, x3)), fe_mul(s1, ppp));
-    acc.zz = fe_mul(fe_mul(acc.zz, q.zz), pp);
-    acc.zzz = fe_mul(fe_mul(acc.zzz, q.zzz), ppp);
+    Fp pp = M::mul(p, p);
+    Fp ppp = M::mul(p, pp);
+    Fp qq = M::mul(u1, pp);
+    Fp x3 = fe_sub(fe_sub(fe_sub(M::mul(r, r), ppp), qq), qq);
+    Fp y3 = fe_sub(M::mul(r, fe_sub(qq, x3)), M::mul(s1, ppp));
+    acc.zz = M::mul(M::mul(acc.zz, q.zz), pp);
+    acc.zzz = M::mul(M::mul(acc.zzz, q.zzz), ppp);
     acc.x = x3; acc.y = y3;
 }
+HD void xyzz_add(G1Xyzz& acc, const G1Xyzz& q) { xyzz_add_t<MulInline>(acc, q); }
 
 // affine normalisation: one inversion for both denominators
 HD G1Affine xyzz_to_affine(const G1Xyzz& a) {
     G1Affine r;
     if (xyzz_is_inf(a)) { r.x = fe_zero<FpParams>(); r.y = fe_zero<FpParams>(); return r; }
-    Fp t = fe_inv(fe_mul(a.zz, a.zzz));
+    Fp t = fe_inv_gcd(fe_mul(a.zz, a.zzz));
     Fp izz = fe_mul(t, a.zzz);
     Fp izzz = fe_mul(t, a.zz);
     r.x = fe_mul(a.x, izz);

@@ -75,27 +75,54 @@ __device__ __forceinline__ void xyzz_st(uint32_t* arr, uint64_t i, const G1Xyzz&
     fp_st(arr + 48 * i + 24, a.zz); fp_st(arr + 48 * i + 36, a.zzz);
 }
 
-// out-of-line copies of the point operations for the short tail kernels (reduce, collapse, combine):
-// they run on few threads, so code size and compile time matter more there than call overhead
-__device__ __noinline__ void xyzz_add_ni(G1Xyzz& acc, const G1Xyzz& q) { xyzz_add(acc, q); }
-__device__ __noinline__ void xyzz_dbl_ni(G1Xyzz& acc) { xyzz_dbl(acc); }
-__device__ __noinline__ void xyzz_add_mixed_ni(G1Xyzz& acc, const G1Affine& q, bool neg) { xyzz_add_mixed(acc, q, neg); }
-__device__ __noinline__ Fp fp_mul_ni(const Fp& a, const Fp& b) { return fe_mul(a, b); }
-__device__ __noinline__ Fp fp_inv_ni(const Fp& a) {
-    Fp acc = fe_one<FpParams>();
-    for (int i = 12 * 32 - 1; i >= 0; i--) {
-        acc = fp_mul_ni(acc, acc);
-        if ((FpParams::pm2(i >> 5) >> (i & 31)) & 1) acc = fp_mul_ni(acc, a);
-    }
-    return acc;
-}
-__device__ __noinline__ G1Affine xyzz_to_affine_ni(const G1Xyzz& a) {
+// Out-of-line field product: the point formulas of every kernel except the fully inlined accumulate
+// variants call it, so a point addition is ~14 calls plus glue instead of ~75 KB of unrolled
+// IMAD chains -- the code stays in the instruction cache and compiles in seconds.
+__device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) { return fe_mul(a, b); }
+struct MulCall {
+    static __device__ __forceinline__ Fp mul(const Fp& a, const Fp& b) { return fp_mul_call(a, b); }
+};
+__device__ __forceinline__ Fp fp_mul_ni(const Fp& a, const Fp& b) { return fp_mul_call(a, b); }
+__device__ __forceinline__ void xyzz_add_ni(G1Xyzz& acc, const G1Xyzz& q) { xyzz_add_t<MulCall>(acc, q); }
+__device__ __forceinline__ void xyzz_dbl_ni(G1Xyzz& acc) { xyzz_dbl_t<MulCall>(acc); }
+// binary-GCD inversion, out of line (one call site per kernel)
+__device__ __noinline__ Fp fp_inv_ni(Fp a) { return fe_inv_gcd(a); }
+__device__ __forceinline__ G1Affine xyzz_to_affine_ni(const G1Xyzz& a) {
     G1Affine r;
     if (xyzz_is_inf(a)) { r.x = fe_zero<FpParams>(); r.y = fe_zero<FpParams>(); return r; }
     Fp t = fp_inv_ni(fp_mul_ni(a.zz, a.zzz));
     r.x = fp_mul_ni(a.x, fp_mul_ni(t, a.zzz));
     r.y = fp_mul_ni(a.y, fp_mul_ni(t, a.zz));
     return r;
+}
+// acc += (neg ? -q : q); same formulas as xyzz_add_mixed, ordered to keep few values live
+template <class M>
+__device__ __forceinline__ void xyzz_add_mixed_t(G1Xyzz& acc, const G1Affine& q, bool neg) {
+    if (g1a_is_inf(q)) return;
+    Fp qy = neg ? fe_neg(q.y) : q.y;
+    if (xyzz_is_inf(acc)) {
+        acc.x = q.x; acc.y = qy; acc.zz = fe_one<FpParams>(); acc.zzz = fe_one<FpParams>();
+        return;
+    }
+    Fp p = fe_sub(M::mul(q.x, acc.zz), acc.x);
+    Fp r = fe_sub(M::mul(qy, acc.zzz), acc.y);
+    if (fe_is_zero(p)) {
+        if (fe_is_zero(r)) xyzz_dbl_affine(acc, q.x, qy);  // same point (cold: inlined code that is never fetched)
+        else xyzz_set_inf(acc);
+        return;
+    }
+    Fp pp = M::mul(p, p);
+    Fp qq = M::mul(acc.x, pp);
+    acc.zz = M::mul(acc.zz, pp);
+    Fp ppp = M::mul(p, pp);
+    acc.zzz = M::mul(acc.zzz, ppp);
+    Fp t = M::mul(acc.y, ppp);
+    Fp x3 = fe_sub(fe_sub(fe_sub(M::mul(r, r), ppp), qq), qq);
+    acc.y = fe_sub(M::mul(r, fe_sub(qq, x3)), t);
+    acc.x = x3;
+}
+__device__ __forceinline__ void xyzz_add_mixed_ni(G1Xyzz& acc, const G1Affine& q, bool neg) {
+    xyzz_add_mixed_t<MulCall>(acc, q, neg);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -235,40 +262,6 @@ __global__ void msm_task_order_kernel(const uint32_t* task_len, const uint32_t* 
 //    1 = inlined, capped for 3 CTAs/SM; 2 = inlined, capped for 4 CTAs/SM;
 //    3 = products out of line (small loop body that stays in the instruction cache), 4 CTAs/SM.
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) { return fe_mul(a, b); }
-struct MulInline {
-    static __device__ __forceinline__ Fp mul(const Fp& a, const Fp& b) { return fe_mul(a, b); }
-};
-struct MulCall {
-    static __device__ __forceinline__ Fp mul(const Fp& a, const Fp& b) { return fp_mul_call(a, b); }
-};
-// acc += (neg ? -q : q); same formulas as xyzz_add_mixed, ordered to keep few values live
-template <class M>
-__device__ __forceinline__ void xyzz_add_mixed_t(G1Xyzz& acc, const G1Affine& q, bool neg) {
-    if (g1a_is_inf(q)) return;
-    Fp qy = neg ? fe_neg(q.y) : q.y;
-    if (xyzz_is_inf(acc)) {
-        acc.x = q.x; acc.y = qy; acc.zz = fe_one<FpParams>(); acc.zzz = fe_one<FpParams>();
-        return;
-    }
-    Fp p = fe_sub(M::mul(q.x, acc.zz), acc.x);
-    Fp r = fe_sub(M::mul(qy, acc.zzz), acc.y);
-    if (fe_is_zero(p)) {
-        if (fe_is_zero(r)) xyzz_dbl_affine(acc, q.x, qy);
-        else xyzz_set_inf(acc);
-        return;
-    }
-    Fp pp = M::mul(p, p);
-    Fp qq = M::mul(acc.x, pp);
-    acc.zz = M::mul(acc.zz, pp);
-    Fp ppp = M::mul(p, pp);
-    acc.zzz = M::mul(acc.zzz, ppp);
-    Fp t = M::mul(acc.y, ppp);
-    Fp x3 = fe_sub(fe_sub(fe_sub(M::mul(r, r), ppp), qq), qq);
-    acc.y = fe_sub(M::mul(r, fe_sub(qq, x3)), t);
-    acc.x = x3;
-}
-
 template <int VARIANT>
 __device__ __forceinline__ void msm_accumulate_body(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ entries,
                                                     const uint32_t* __restrict__ task_bucket,
@@ -389,12 +382,81 @@ __global__ void __launch_bounds__(64) msm_reduce_kernel(const uint32_t* __restri
     xyzz_st(A_out, (uint64_t)w * m_out + g, asum);
 }
 
+// Same recurrence, one WARP per group of 32 nodes, for the upper levels of the tree where there are
+// too few groups to fill the machine and the serial 3x16 additions of a thread would be pure latency:
+// suffix sums by a 5-step scan over lanes, T and sum(A) by 5-step butterflies (15 dependent additions
+// instead of 47).  scale_log advances by 5 per level.
+__device__ __forceinline__ G1Xyzz xyzz_shfl_down(const G1Xyzz& v, int d) {
+    G1Xyzz r;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        r.x.l[k] = __shfl_down_sync(0xffffffffu, v.x.l[k], d);
+        r.y.l[k] = __shfl_down_sync(0xffffffffu, v.y.l[k], d);
+        r.zz.l[k] = __shfl_down_sync(0xffffffffu, v.zz.l[k], d);
+        r.zzz.l[k] = __shfl_down_sync(0xffffffffu, v.zzz.l[k], d);
+    }
+    return r;
+}
+__device__ __forceinline__ G1Xyzz xyzz_shfl_xor(const G1Xyzz& v, int d) {
+    G1Xyzz r;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        r.x.l[k] = __shfl_xor_sync(0xffffffffu, v.x.l[k], d);
+        r.y.l[k] = __shfl_xor_sync(0xffffffffu, v.y.l[k], d);
+        r.zz.l[k] = __shfl_xor_sync(0xffffffffu, v.zz.l[k], d);
+        r.zzz.l[k] = __shfl_xor_sync(0xffffffffu, v.zzz.l[k], d);
+    }
+    return r;
+}
+constexpr int COOP_LOG = 5, COOP_RADIX = 32;
+__global__ void __launch_bounds__(128) msm_reduce_coop_kernel(const uint32_t* __restrict__ S_in, const uint32_t* __restrict__ A_in,
+                                                              uint32_t* __restrict__ S_out, uint32_t* __restrict__ A_out,
+                                                              uint32_t m_in, uint32_t m_out, uint32_t nwin, uint32_t scale_log) {
+    uint32_t warp = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (warp >= m_out * nwin) return;                      // whole warps leave together
+    uint32_t w = warp / m_out, g = warp % m_out;
+    uint64_t base = (uint64_t)w * m_in + (uint64_t)g * COOP_RADIX;
+    uint32_t cnt = min((uint32_t)COOP_RADIX, m_in - g * COOP_RADIX);
+    G1Xyzz run;
+    if (lane < cnt) run = xyzz_ld(S_in, base + lane);
+    else xyzz_set_inf(run);
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {                      // run_i = sum_{i' >= i} S_i'
+        G1Xyzz o = xyzz_shfl_down(run, d);
+        if (lane + d < 32) xyzz_add_ni(run, o);
+    }
+    G1Xyzz T;                                               // T = sum_{i >= 1} run_i = sum_i i * S_i
+    if (lane >= 1) T = run;
+    else xyzz_set_inf(T);
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        G1Xyzz o = xyzz_shfl_xor(T, d);
+        xyzz_add_ni(T, o);
+    }
+    G1Xyzz asum;
+    if (A_in) {
+        if (lane < cnt) asum = xyzz_ld(A_in, base + lane);
+        else xyzz_set_inf(asum);
+#pragma unroll 1
+        for (int d = 16; d >= 1; d >>= 1) {
+            G1Xyzz o = xyzz_shfl_xor(asum, d);
+            xyzz_add_ni(asum, o);
+        }
+    } else asum = run;                                      // level 0: A_i = S_i, lane 0 holds their sum
+    if (lane == 0) {
+        for (uint32_t k = 0; k < scale_log; k++) xyzz_dbl_ni(T);
+        xyzz_add_ni(asum, T);
+        xyzz_st(S_out, (uint64_t)w * m_out + g, run);
+        xyzz_st(A_out, (uint64_t)w * m_out + g, asum);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // 8. window combine + affine normalisation.  out_mont: 24 limbs Montgomery affine;
 //    out_canon: 24 limbs canonical (the wire format), either may be null.
 // ---------------------------------------------------------------------------------------
 __global__ void msm_combine_kernel(const uint32_t* __restrict__ win_sums, uint32_t W, uint32_t c,
-                                   uint32_t* out_mont, uint32_t* out_canon) {
+                                   uint32_t* out_mont, uint32_t* out_canon, uint32_t* out_xyzz) {
     if (threadIdx.x != 0) return;
     const uint32_t b = blockIdx.x;             // one block per batch item
     G1Xyzz acc;
@@ -404,11 +466,26 @@ __global__ void msm_combine_kernel(const uint32_t* __restrict__ win_sums, uint32
         G1Xyzz s = xyzz_ld(win_sums, (uint64_t)b * W + w);
         xyzz_add_ni(acc, s);
     }
+    if (out_xyzz) xyzz_st(out_xyzz, b, acc);               // un-normalised partial (multi-GPU exchange)
+    if (!out_mont && !out_canon) return;
     G1Affine a = xyzz_to_affine_ni(acc);
     if (out_mont) { fp_st(out_mont + 24 * b, a.x); fp_st(out_mont + 24 * b + 12, a.y); }
     if (out_canon) { fp_st(out_canon + 24 * b, fe_from_mont(a.x)); fp_st(out_canon + 24 * b + 12, fe_from_mont(a.y)); }
 }
 
+// sum of n XYZZ partial points -> affine: the combine step of the point-range sharded MSM
+__global__ void g1_sum_xyzz_kernel(const uint32_t* __restrict__ pts, uint32_t n, uint32_t* out_mont, uint32_t* out_canon) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    G1Xyzz acc;
+    xyzz_set_inf(acc);
+    for (uint32_t i = 0; i < n; i++) {
+        G1Xyzz p = xyzz_ld(pts, i);
+        xyzz_add_ni(acc, p);
+    }
+    G1Affine a = xyzz_to_affine_ni(acc);
+    if (out_mont) { fp_st(out_mont, a.x); fp_st(out_mont + 12, a.y); }
+    if (out_canon) { fp_st(out_canon, fe_from_mont(a.x)); fp_st(out_canon + 12, fe_from_mont(a.y)); }
+}
 // sum of n affine points (Montgomery form) -> affine; used to combine per-GPU partial results
 __global__ void g1_sum_kernel(const uint32_t* __restrict__ pts, uint32_t n, uint32_t* out_mont, uint32_t* out_canon) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;

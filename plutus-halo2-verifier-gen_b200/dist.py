@@ -2,8 +2,8 @@
 
 MSM is linear in the point set, so rank r keeps the slice [r*n/G, (r+1)*n/G) of the SRS table
 resident, receives the matching slice of the scalars, runs the whole Pippenger pipeline locally
-down to one affine point, and the G partial points (96 bytes each) are exchanged with one
-all-gather over NVLink and summed on the device (``b200zk_g1_sum_dev``).  One process per GPU;
+down to one un-normalised point, and the G partial points (192 bytes each, extended Jacobian) are
+exchanged with one all-gather over NVLink and folded on the device (``b200zk_g1_sum_partials_dev``).  One process per GPU;
 ``torch.distributed`` is the plumbing (NCCL on GPUs, gloo in the CPU tests of the host logic).
 
 Batches of independent polynomials are split by :func:`split_batch` with no collective at all.
@@ -41,8 +41,8 @@ class ShardedMSM:
         self.h = bases_handle
         self.n_local = n_local
         self.rank, self.world, self.group = rank, world, group
-        self.d_part = torch.zeros(96, dtype=torch.uint8, device="cuda")
-        self.d_all = torch.zeros(96 * world, dtype=torch.uint8, device="cuda")
+        self.d_part = torch.zeros(192, dtype=torch.uint8, device="cuda")           # XYZZ partial of this rank
+        self.d_all = torch.zeros(192 * world, dtype=torch.uint8, device="cuda")
         self.d_out = torch.zeros(96, dtype=torch.uint8, device="cuda")
         self.d_scalars = None
 
@@ -55,10 +55,10 @@ class ShardedMSM:
             check(lib().b200zk_msm_g1_dev(self.h, 0, d_scalars.data_ptr(), self.n_local, 1, scalar_fmt, 0,
                                           self.d_out.data_ptr(), st))
             return self.d_out
-        check(lib().b200zk_msm_g1_dev(self.h, 0, d_scalars.data_ptr(), self.n_local, 1, scalar_fmt,
-                                      self.d_part.data_ptr(), 0, st))
+        check(lib().b200zk_msm_g1_partial_dev(self.h, 0, d_scalars.data_ptr(), self.n_local, scalar_fmt,
+                                              self.d_part.data_ptr(), st))
         torch.distributed.all_gather_into_tensor(self.d_all, self.d_part, group=self.group)
-        check(lib().b200zk_g1_sum_dev(self.d_all.data_ptr(), self.world, 0, self.d_out.data_ptr(), st))
+        check(lib().b200zk_g1_sum_partials_dev(self.d_all.data_ptr(), self.world, 0, self.d_out.data_ptr(), st))
         return self.d_out
 
     def run_host(self, h_scalars_pinned, h_out_pinned, scalar_fmt: int = capi.FMT_CANONICAL) -> None:

@@ -54,6 +54,10 @@ template <class P> static int check_field(const char* name,
             r = fe_from_mont(fe_inv(am)); oinv((uint8_t*)a.l, (uint8_t*)e.l);
             if (!fe_eq(r, e)) { bad++; printf("%s inv mismatch it=%d\n", name, it); }
         }
+        if (it < 3000 && !fe_is_zero(a)) {
+            r = fe_from_mont(fe_inv_gcd(am)); oinv((uint8_t*)a.l, (uint8_t*)e.l);
+            if (!fe_eq(r, e)) { bad++; if (bad < 5) printf("%s inv_gcd mismatch it=%d\n", name, it); }
+        }
     }
     printf("%s: %s\n", name, bad ? "FAIL" : "ok");
     return bad;

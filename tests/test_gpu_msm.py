@@ -286,3 +286,38 @@ def test_g1_sum_dev(gpu, oracle):
     gpu.capi.check(gpu.lib().b200zk_g1_sum_dev(d.data_ptr(), n, 0, d_out.data_ptr(), st))
     torch.cuda.synchronize()
     assert bytes(d_out.cpu().numpy()) == oracle.g1_sum(pts, n)
+
+
+def test_sharded_partials_emulated_on_one_gpu(gpu, oracle):
+    """The N > 1 data path on one device: two 'ranks' each hold a slice of the table, compute an
+    un-normalised XYZZ partial (b200zk_msm_g1_partial_dev), the partials are concatenated as the
+    all-gather would and folded by b200zk_g1_sum_partials_dev."""
+    import importlib
+    import torch
+    zdist = importlib.import_module("plutus-halo2-verifier-gen_b200.dist")
+    n, world = 5001, 2
+    pts = oracle.synth_bases(0xB500, 0, n)
+    sc = oracle.synth_scalars(21, 0, n)
+    st = torch.cuda.current_stream().cuda_stream
+    d_all = torch.zeros(192 * world, dtype=torch.uint8, device="cuda")
+    handles = []
+    for r in range(world):
+        s, e = zdist.shard_range(n, r, world)
+        h = register(gpu, pts[96 * s:96 * e], e - s)
+        handles.append(h)
+        d_sc = torch.frombuffer(bytearray(sc[32 * s:32 * e]), dtype=torch.uint8).cuda()
+        gpu.capi.check(gpu.lib().b200zk_msm_g1_partial_dev(h, 0, d_sc.data_ptr(), e - s, 0, d_all[192 * r:].data_ptr(), st))
+        torch.cuda.synchronize()
+    d_out = torch.zeros(96, dtype=torch.uint8, device="cuda")
+    gpu.capi.check(gpu.lib().b200zk_g1_sum_partials_dev(d_all.data_ptr(), world, 0, d_out.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert bytes(d_out.cpu().numpy()) == oracle.msm(pts, sc, n)
+    # ShardedMSM with world = 1 goes through the same entry points
+    m = zdist.ShardedMSM(handles[0], zdist.shard_range(n, 0, world)[1], 0, 1)
+    s0, e0 = zdist.shard_range(n, 0, world)
+    d_sc = torch.frombuffer(bytearray(sc[:32 * e0]), dtype=torch.uint8).cuda()
+    out = m.run_device(d_sc)
+    torch.cuda.synchronize()
+    assert bytes(out.cpu().numpy()) == oracle.msm(pts[:96 * e0], sc[:32 * e0], e0)
+    for h in handles:
+        gpu.capi.check(gpu.lib().b200zk_bases_release(h))
