@@ -452,6 +452,8 @@ int32_t ntt_run(uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t 
     if (!attr_set) {
         CU(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
         CU(cudaFuncSetAttribute(ntt_pass_kernel_occ2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+        CU(cudaFuncSetAttribute(ntt_pass_kernel_call2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+        CU(cudaFuncSetAttribute(ntt_pass_kernel_call3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
         if (const char* v = getenv("B200ZK_NTT_VARIANT")) ntt_variant = atoi(v);
         attr_set = true;
     }
@@ -480,6 +482,8 @@ int32_t ntt_run(uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t 
         a.total_cols = (uint64_t)batch << a.log_cols;
         uint64_t ctas = (total + NTT_B - 1) / NTT_B;
         if (ntt_variant == 0) LAUNCH(ntt_pass_kernel, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+        else if (ntt_variant == 2) LAUNCH(ntt_pass_kernel_call2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+        else if (ntt_variant == 3) LAUNCH(ntt_pass_kernel_call3, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         else LAUNCH(ntt_pass_kernel_occ2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         TRY(prof_mark((int)i + 1, s));
         src = dst;

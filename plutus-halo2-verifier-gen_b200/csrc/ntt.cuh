@@ -79,9 +79,18 @@ __device__ __forceinline__ void ntt_st(uint32_t* p, const Fr& v) {
     q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
+// Fr product, inlined or out of line (smaller loop bodies that stay in the instruction cache)
+__device__ __noinline__ Fr fr_mul_call(Fr a, Fr b) { return fe_mul(a, b); }
+struct FrMulInline {
+    static __device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) { return fe_mul(a, b); }
+};
+struct FrMulCall {
+    static __device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) { return fr_mul_call(a, b); }
+};
+
 // radix-2 DIF stages on index bits lb+NB-1 .. lb of the CTA-local array; the thread owns the 8
 // elements whose index differs in bits lb..lb+2.
-template <int NB>
+template <int NB, class M>
 __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restrict__ tw_local, uint32_t deg,
                                           uint32_t lb, uint32_t tid) {
     // lanes walk the low index bits when that is conflict-free (lb >= 5), else the high bits
@@ -112,7 +121,7 @@ __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restri
             } else {
                 uint32_t il = (base | ((uint32_t)j << lb)) & rmask;
                 uint32_t e = (il & ((1u << b) - 1)) << (deg - 1 - b);
-                v[j | (1 << q)] = fe_mul(d, ntt_ldg(tw_local + 8 * (size_t)e));
+                v[j | (1 << q)] = M::mul(d, ntt_ldg(tw_local + 8 * (size_t)e));
             }
         }
     }
@@ -120,6 +129,7 @@ __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restri
     for (int j = 0; j < 8; j++) ntt_sts(sm, base | ((uint32_t)j << lb), v[j]);
 }
 
+template <class M>
 __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     extern __shared__ uint32_t sm[];
     const uint32_t tid = threadIdx.x;
@@ -141,7 +151,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
             uint64_t gi = (poly << a.log_n) + u + ((uint64_t)j << a.log_cols);
             v = ntt_ld(a.in + 8 * gi);
             if (a.reduce_in) fe_reduce_loose(v);
-            if (a.in_scale) v = fe_mul(v, ntt_ldg(a.in_scale + 8 * (u + ((uint64_t)j << a.log_cols))));
+            if (a.in_scale) v = M::mul(v, ntt_ldg(a.in_scale + 8 * (u + ((uint64_t)j << a.log_cols))));
         }
         ntt_sts(sm, (ul << deg) | j, v);
     }
@@ -152,9 +162,9 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     while (rem > 0) {
         int nb = rem >= 3 ? 3 : rem;
         uint32_t lb = (uint32_t)(rem - nb);
-        if (nb == 3) ntt_group<3>(sm, a.tw_local, deg, lb, tid);
-        else if (nb == 2) ntt_group<2>(sm, a.tw_local, deg, lb, tid);
-        else ntt_group<1>(sm, a.tw_local, deg, lb, tid);
+        if (nb == 3) ntt_group<3, M>(sm, a.tw_local, deg, lb, tid);
+        else if (nb == 2) ntt_group<2, M>(sm, a.tw_local, deg, lb, tid);
+        else ntt_group<1, M>(sm, a.tw_local, deg, lb, tid);
         __syncthreads();
         rem -= nb;
     }
@@ -175,17 +185,19 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
         Fr v = ntt_lds(sm, (ul << deg) | kr);
         uint64_t poly = col >> a.log_cols, u = col & cmask;
         uint64_t q = u & (((uint64_t)1 << a.log_s) - 1), p = u >> a.log_s;
-        if (a.tw_pass) v = fe_mul(v, ntt_ldg(a.tw_pass + 8 * ((p << deg) + k)));
+        if (a.tw_pass) v = M::mul(v, ntt_ldg(a.tw_pass + 8 * ((p << deg) + k)));
         uint64_t oi = q + (((p << deg) + k) << a.log_s);
-        if (a.out_scale) v = fe_mul(v, ntt_ldg(a.out_scale + 8 * oi));
-        if (a.scalar) v = fe_mul(v, ntt_ldg(a.scalar));
+        if (a.out_scale) v = M::mul(v, ntt_ldg(a.out_scale + 8 * oi));
+        if (a.scalar) v = M::mul(v, ntt_ldg(a.scalar));
         ntt_st(a.out + 8 * ((poly << a.log_n) + oi), v);
     }
 }
 
 // one CTA per SM (registers unconstrained) and two CTAs per SM (<= 128 registers); the plan picks
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) { ntt_pass_body(a); }
-__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_occ2(NttPassArgs a) { ntt_pass_body(a); }
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) { ntt_pass_body<FrMulInline>(a); }
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_occ2(NttPassArgs a) { ntt_pass_body<FrMulInline>(a); }
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_call2(NttPassArgs a) { ntt_pass_body<FrMulCall>(a); }
+__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel_call3(NttPassArgs a) { ntt_pass_body<FrMulCall>(a); }
 
 // out[i] = scale * base^(e0 + i*mult mod 2^64), generic table generator (Montgomery form in and out).
 // kind 0: exponent = i * mult.  kind 1 (pass table): i = p*R + k, exponent = mult * p * k.

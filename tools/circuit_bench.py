@@ -1,0 +1,148 @@
+"""Replays the MSM + NTT call trace of one create_proof through the C ABI for the reference's
+example circuits (shapes from SURVEY.md section 3.2 / 8d: commitments per proof from
+/root/reference/docs/verifier_math.js:84-93 and the per-example counts at
+examples/simple_mul.rs:91-92, atms.rs:85-86, atms_with_lookups.rs:110-111, ivc.rs:243-244).
+
+The reference's prover cannot run here (no Rust), so this is the replay SURVEY 8d prescribes for the
+"create_proof ms" metric: every commitment becomes one MSM of n = 2^k scalars against a resident
+table (advice-like columns use the prover-like distribution S, quotient pieces / f / pi uniform),
+every committed column costs one inverse NTT of size n and one coset NTT of size 2^(k+2), plus
+one inverse coset NTT for the quotient.  CPU column: the checker's C port on all host threads
+(one MSM and one NTT of each size timed, scaled by the call counts).
+
+usage: python tools/circuit_bench.py [--circuits simple_mul,atms17,...] [--no-cpu]
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (scalar generator, oracle loader)
+
+#            name: (k, proof commitments, of which uniform (h pieces + f + pi + random poly))
+CIRCUITS = {
+    "simple_mul": (5, 10, 5),
+    "lookup_table": (11, 20, 6),
+    "atms14": (14, 18, 6),
+    "atms17": (17, 18, 6),
+    "atms19": (19, 18, 6),
+    "atms_lookups17": (17, 22, 6),
+    "sha256_19": (19, 26, 7),
+    "ivc19": (19, 43, 7),
+}
+
+
+def prover_like(np, seed, n):
+    """distribution S: 70% in {0,1}, 20% < 2^16, 10% uniform; the last 6 rows are blinding (uniform)"""
+    rng = np.random.default_rng(seed)
+    u = rng.random(n)
+    k = bench.synth_scalars_np(seed, 0, n)
+    small = rng.integers(0, 1 << 16, n, dtype=np.uint64)
+    bit = rng.integers(0, 2, n, dtype=np.uint64)
+    m1, m2 = u < 0.7, (u >= 0.7) & (u < 0.9)
+    m1[-6:] = False
+    m2[-6:] = False
+    k[m1, 0] = bit[m1]
+    k[m2, 0] = small[m2]
+    k[m1 | m2, 1:] = 0
+    return k
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--circuits", default=",".join(CIRCUITS))
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+
+    zk = importlib.import_module("plutus-halo2-verifier-gen_b200")
+    zk.init(0)
+    lib = zk.lib()
+    L = None if args.no_cpu else bench.load_oracle()
+    st = torch.cuda.current_stream().cuda_stream
+    for name in args.circuits.split(","):
+        k, ncom, nuni = CIRCUITS[name]
+        n = 1 << k
+        ek = k + 2
+        # SRS table (synthetic, generated on the device) -> resident handle with window tables
+        d_b = torch.empty(96 * n, dtype=torch.uint8, device="cuda")
+        zk.capi.check(lib.b200zk_g1_synth_bases_dev(0xB200, 0, n, d_b.data_ptr(), st))
+        torch.cuda.synchronize()
+        h = C.c_uint64(0)
+        zk.capi.check(lib.b200zk_bases_register_dev(d_b.data_ptr(), n, zk.FMT_MONT, 96, C.byref(h)))
+        cols = [prover_like(np, 100 + i, n) for i in range(ncom - nuni)] + \
+               [bench.synth_scalars_np(200 + i, 0, n) for i in range(nuni)]
+        sc = torch.from_numpy(np.concatenate(cols).view(np.uint8).reshape(-1)).pin_memory()
+        out = torch.zeros(96 * ncom, dtype=torch.uint8).pin_memory()
+        omega_inv = pow(pow(zk.host.ROOT_OF_UNITY, 1 << (32 - k), zk.host.R_MOD), zk.host.R_MOD - 2, zk.host.R_MOD).to_bytes(32, "little")
+        omega_ext = pow(zk.host.ROOT_OF_UNITY, 1 << (32 - ek), zk.host.R_MOD)
+        omega_ext_b = omega_ext.to_bytes(32, "little")
+        omega_ext_inv = pow(omega_ext, zk.host.R_MOD - 2, zk.host.R_MOD).to_bytes(32, "little")
+        g = zk.host.ZETA.to_bytes(32, "little")
+        gi = pow(zk.host.ZETA, zk.host.R_MOD - 2, zk.host.R_MOD).to_bytes(32, "little")
+        ncols = ncom - 3                                   # columns that go through the domain transforms
+        lag = torch.from_numpy(np.concatenate(cols[:ncols]).view(np.uint8).reshape(-1)).pin_memory()
+        ext = torch.zeros(32 * (1 << ek) * ncols, dtype=torch.uint8).pin_memory()
+
+        def gpu_trace():
+            # all commitments of the proof: one batched MSM call (host buffers in, 96-byte points out)
+            zk.capi.check(lib.b200zk_msm_g1_batch(h.value, 0, sc.data_ptr(), n, ncom, 0, out.data_ptr()))
+            # lagrange_to_coeff for every column, then coeff_to_extended, then one extended_to_coeff
+            zk.capi.check(lib.b200zk_ntt_fr_batch(lag.data_ptr(), ncols, k, zk.capi.addr(omega_inv), zk.NTT_INVERSE_SCALE, 0))
+            zk.capi.check(lib.b200zk_ntt_fr_batch(ext.data_ptr(), ncols, ek, zk.capi.addr(omega_ext_b), zk.NTT_COSET_IN, zk.capi.addr(g)))
+            zk.capi.check(lib.b200zk_ntt_fr_batch(ext.data_ptr(), 1, ek, zk.capi.addr(omega_ext_inv),
+                                                  zk.NTT_INVERSE_SCALE | zk.NTT_COSET_OUT, zk.capi.addr(gi)))
+
+        gpu_trace()
+        l0 = zk.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(args.reps):
+            gpu_trace()
+        gpu_ms = (time.perf_counter() - t0) / args.reps * 1e3
+        launches = (zk.launch_count() - l0) // args.reps
+        # MSM-only and NTT-only split
+        t0 = time.perf_counter()
+        for _ in range(args.reps):
+            zk.capi.check(lib.b200zk_msm_g1_batch(h.value, 0, sc.data_ptr(), n, ncom, 0, out.data_ptr()))
+        msm_ms = (time.perf_counter() - t0) / args.reps * 1e3
+        rec = {"circuit": name, "k": k, "commitments": ncom, "ntt_columns": ncols, "gpu_trace_ms": gpu_ms, "gpu_msm_ms": msm_ms,
+               "gpu_ntt_ms": gpu_ms - msm_ms, "gpu_launches": launches, "timed": "host clock, host buffers in and out"}
+        if L is not None:
+            bases = np.empty(96 * n, dtype=np.uint8)
+            L.orc_g1_synth_bases(0xB200, 0, n, bases.ctypes.data, 0)
+            o = np.zeros(96, dtype=np.uint8)
+            tt = []
+            for col in (cols[0], cols[-1]):               # one prover-like and one uniform commitment
+                t0 = time.perf_counter()
+                L.orc_g1_msm(bases.ctypes.data, col.ctypes.data, n, o.ctypes.data, 0)
+                tt.append(time.perf_counter() - t0)
+            rec["parity_first_commitment"] = None
+            L.orc_g1_msm(bases.ctypes.data, cols[0].ctypes.data, n, o.ctypes.data, 0)
+            rec["parity_first_commitment"] = bytes(out[:96].numpy()) == bytes(o)
+            cpu_msm = tt[0] * (ncom - nuni) + tt[1] * nuni
+            buf = cols[-1].copy()
+            t0 = time.perf_counter()
+            L.orc_ntt(buf.ctypes.data, k, omega_inv, 1, None, None, 0)
+            t_small = time.perf_counter() - t0
+            big = np.zeros((1 << ek, 4), dtype=np.uint64)
+            big[:n] = cols[-1]
+            t0 = time.perf_counter()
+            L.orc_ntt(big.ctypes.data, ek, omega_ext_b, 0, g, None, 0)
+            t_big = time.perf_counter() - t0
+            cpu_ntt = t_small * ncols + t_big * (ncols + 1)
+            rec.update({"cpu_trace_ms": (cpu_msm + cpu_ntt) * 1e3, "cpu_msm_ms": cpu_msm * 1e3, "cpu_ntt_ms": cpu_ntt * 1e3,
+                        "cpu_cores": L.orc_max_threads(), "cpu_kind": "port (checker's C restatement, sampled: 2 MSMs + 2 NTTs scaled by call counts)"})
+        print(json.dumps(rec), flush=True)
+        zk.capi.check(lib.b200zk_bases_release(h.value))
+        del d_b
+
+
+if __name__ == "__main__":
+    main()
