@@ -123,7 +123,7 @@ struct Ctx {
     MsmPlan last_plan{};
     // MSM workspace
     DevBuf scalars, counts, offsets, cursor, ntask, task_off, entries, task_bucket, task_start, task_len, buckets,
-        partials, len_hist, len_off, order, heavy, redS[2], redA[2], scan_tmp[2], out_mont, out_canon, stage, flag;
+        partials, len_hist, len_off, order, heavy, aff_a, aff_b, aff_pre, redS[2], redA[2], scan_tmp[2], out_mont, out_canon, stage, flag;
     // NTT workspace
     DevBuf ntt_data, ntt_tmp[2], small;
 };
@@ -290,6 +290,20 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
             case 1: LAUNCH(msm_accumulate_kernel_v1, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
             case 2: LAUNCH(msm_accumulate_kernel_v2, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
             case 3: LAUNCH(msm_accumulate_kernel_v3, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
+            case 4:
+            case 5: {
+                size_t slots = max_entries / 2 + 2;
+                TRY(g.aff_a.ensure(slots * 96));
+                TRY(g.aff_b.ensure(slots * 96));
+                TRY(g.aff_pre.ensure(slots * 48));
+                if (g.tune_variant == 4)
+                    LAUNCH(msm_accumulate_affine_kernel, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials,
+                           g.aff_a.as<uint32_t>(), g.aff_b.as<uint32_t>(), g.aff_pre.as<uint32_t>());
+                else
+                    LAUNCH(msm_accumulate_affine_kernel_r168, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials,
+                           g.aff_a.as<uint32_t>(), g.aff_b.as<uint32_t>(), g.aff_pre.as<uint32_t>());
+                break;
+            }
             default: LAUNCH(msm_accumulate_kernel, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
         }
     }
@@ -736,7 +750,7 @@ int32_t b200zk_shutdown(void) {
     g.coset_tables.clear();
     if (g.fixed_table) { cudaFree(g.fixed_table); g.fixed_table = nullptr; }
     DevBuf* all[] = {&g.scalars, &g.counts, &g.offsets, &g.cursor, &g.ntask, &g.task_off, &g.entries, &g.task_bucket,
-                     &g.task_start, &g.task_len, &g.buckets, &g.partials, &g.len_hist, &g.len_off, &g.order, &g.heavy, &g.redS[0], &g.redS[1], &g.redA[0], &g.redA[1],
+                     &g.task_start, &g.task_len, &g.buckets, &g.partials, &g.len_hist, &g.len_off, &g.order, &g.heavy, &g.aff_a, &g.aff_b, &g.aff_pre, &g.redS[0], &g.redS[1], &g.redA[0], &g.redA[1],
                      &g.scan_tmp[0], &g.scan_tmp[1], &g.out_mont, &g.out_canon, &g.stage, &g.flag, &g.ntt_data,
                      &g.ntt_tmp[0], &g.ntt_tmp[1], &g.small};
     for (DevBuf* b : all) b->release();

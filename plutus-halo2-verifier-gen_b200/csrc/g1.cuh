@@ -101,6 +101,36 @@ HD void xyzz_add_mixed(G1Xyzz& acc, const G1Affine& q, bool neg) {
     acc.x = x3; acc.y = y3;
 }
 
+// acc += q for an affine q whose sign is already applied; products through the policy M
+// (same formulas as xyzz_add_mixed, ordered to keep few values live)
+template <class M> HD void xyzz_add_mixed_pol(G1Xyzz& acc, const G1Affine& q) {
+    if (g1a_is_inf(q)) return;
+    if (xyzz_is_inf(acc)) {
+        acc.x = q.x; acc.y = q.y; acc.zz = fe_one<FpParams>(); acc.zzz = fe_one<FpParams>();
+        return;
+    }
+    Fp p = fe_sub(M::mul(q.x, acc.zz), acc.x);
+    Fp r = fe_sub(M::mul(q.y, acc.zzz), acc.y);
+    if (fe_is_zero(p)) {
+        if (fe_is_zero(r)) {
+            G1Xyzz d;
+            d.x = q.x; d.y = q.y; d.zz = fe_one<FpParams>(); d.zzz = fe_one<FpParams>();
+            xyzz_dbl_t<M>(d);
+            acc = d;
+        } else xyzz_set_inf(acc);
+        return;
+    }
+    Fp pp = M::mul(p, p);
+    Fp qq = M::mul(acc.x, pp);
+    acc.zz = M::mul(acc.zz, pp);
+    Fp ppp = M::mul(p, pp);
+    acc.zzz = M::mul(acc.zzz, ppp);
+    Fp t = M::mul(acc.y, ppp);
+    Fp x3 = fe_sub(fe_sub(fe_sub(M::mul(r, r), ppp), qq), qq);
+    acc.y = fe_sub(M::mul(r, fe_sub(qq, x3)), t);
+    acc.x = x3;
+}
+
 // acc += q, both XYZZ (EFD add-2008-s: 12M + 2S)
 template <class M> HD void xyzz_add_t(G1Xyzz& acc, const G1Xyzz& q) {
     if (xyzz_is_inf(q)) return;

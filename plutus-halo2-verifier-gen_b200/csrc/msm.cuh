@@ -18,6 +18,7 @@
 //   7. reduce    : sum_b b*B_b per window by a radix-16 running-sum tree
 //   8. combine   : Horner over the windows, affine normalisation, wire-format output
 #pragma once
+#include "affine_tree.cuh"
 #include "g1.cuh"
 
 namespace b200zk {
@@ -303,6 +304,37 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(MSM_ACC_ARGS) { msm
 __global__ void __launch_bounds__(128, 3) msm_accumulate_kernel_v1(MSM_ACC_ARGS) { msm_accumulate_body<1>(MSM_ACC_PASS); }
 __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel_v2(MSM_ACC_ARGS) { msm_accumulate_body<2>(MSM_ACC_PASS); }
 __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel_v3(MSM_ACC_ARGS) { msm_accumulate_body<3>(MSM_ACC_PASS); }
+
+// Variants 4/5: batched affine additions (affine_tree.cuh), one thread per task as above.
+__device__ __noinline__ Fp fp_inv_fast_call(Fp a) { return fe_inv_fast(a); }
+struct InvCall {
+    static __device__ __forceinline__ Fp inv(const Fp& a) { return fp_inv_fast_call(a); }
+};
+__device__ __forceinline__ void msm_accumulate_affine_body(MSM_ACC_ARGS, uint32_t* __restrict__ scr_a, uint32_t* __restrict__ scr_b,
+                                                           uint32_t* __restrict__ pre) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *ntasks_p) return;
+    uint32_t t = order[i];
+    uint32_t start = task_start[t], lenf = task_len[t];
+    AffTreeMem mem;
+    mem.bases = bases;
+    mem.entries = entries;
+    mem.scr[0] = scr_a;
+    mem.scr[1] = scr_b;
+    mem.pre = pre;
+    G1Xyzz acc;
+    msm_affine_tree_task<MulCall, InvCall>(mem, start, lenf & 0x7fffffffu, acc);
+    if (lenf & 0x80000000u) xyzz_st(partials, t, acc);
+    else xyzz_st(buckets, task_bucket[t], acc);
+}
+__global__ void __launch_bounds__(128, 4) msm_accumulate_affine_kernel(MSM_ACC_ARGS, uint32_t* __restrict__ scr_a,
+                                                                       uint32_t* __restrict__ scr_b, uint32_t* __restrict__ pre) {
+    msm_accumulate_affine_body(MSM_ACC_PASS, scr_a, scr_b, pre);
+}
+__global__ void __launch_bounds__(128, 3) msm_accumulate_affine_kernel_r168(MSM_ACC_ARGS, uint32_t* __restrict__ scr_a,
+                                                                            uint32_t* __restrict__ scr_b, uint32_t* __restrict__ pre) {
+    msm_accumulate_affine_body(MSM_ACC_PASS, scr_a, scr_b, pre);
+}
 
 // ---------------------------------------------------------------------------------------
 // 6. collapse split buckets: heavy_list holds the buckets that were split into several tasks

@@ -57,6 +57,8 @@ template <class P> static int check_field(const char* name,
         if (it < 3000 && !fe_is_zero(a)) {
             r = fe_from_mont(fe_inv_gcd(am)); oinv((uint8_t*)a.l, (uint8_t*)e.l);
             if (!fe_eq(r, e)) { bad++; if (bad < 5) printf("%s inv_gcd mismatch it=%d\n", name, it); }
+            r = fe_from_mont(fe_inv_fast(am));
+            if (!fe_eq(r, e)) { bad++; if (bad < 5) printf("%s inv_fast mismatch it=%d\n", name, it); }
         }
     }
     printf("%s: %s\n", name, bad ? "FAIL" : "ok");

@@ -97,3 +97,14 @@ def test_device_algorithms_on_host(oracle):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "Fp: ok" in out.stdout and "Fr: ok" in out.stdout and "G1: ok" in out.stdout
+
+
+def test_affine_tree_on_host(oracle):
+    """affine_tree.cuh (batched-affine bucket accumulation: pair tree, shared branch-free inversion,
+    doubling / opposite / identity pairs) compiled for the host against the oracle."""
+    exe = "/tmp/b200zk_host_affine_tree_test"
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-w", "-I", os.path.join(ROOT, "plutus-halo2-verifier-gen_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "host", "host_affine_tree_test.cpp"), "-o", exe,
+                           "-L", os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "affine tree: ok" in out.stdout, out.stdout + out.stderr

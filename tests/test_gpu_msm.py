@@ -110,6 +110,33 @@ def test_edge_points(gpu, oracle, pyref):
         gpu.capi.check(gpu.lib().b200zk_bases_release(hh))
 
 
+@pytest.mark.parametrize("variant", [3, 4, 5])
+def test_edge_cases_every_accumulate_path(gpu, oracle, pyref, variant):
+    """repeated / opposite / identity points and all-equal scalars through the XYZZ path (3) and the
+    batched-affine paths (4, 5), with buckets long enough for several affine rounds"""
+    rnd = random.Random(40 + variant)
+    G = pyref.G1_GEN
+    base = [pyref.g1_mul(G, rnd.randrange(1, R)) for _ in range(12)]
+    pts = []
+    for i in range(2000):
+        q = base[i % 12]
+        if i % 5 == 0:
+            q = pyref.g1_neg(q)
+        if i % 17 == 0:
+            q = pyref.INF
+        pts.append(q)
+    pb = b"".join(pyref.g1_to_wire(p) for p in pts)
+    try:
+        gpu.capi.check(gpu.lib().b200zk_set_msm_tuning(8 | ((variant + 1) << 8), 512))
+        h = register(gpu, pb, 2000)
+        for sc in (fr(3) * 2000, fr(R - 1) * 2000, oracle.synth_scalars(50 + variant, 0, 2000),
+                   b"".join(fr(rnd.randrange(4)) for _ in range(2000))):
+            assert msm(gpu, h, sc, 2000) == oracle.msm(pb, sc, 2000)
+        gpu.capi.check(gpu.lib().b200zk_bases_release(h))
+    finally:
+        gpu.lib().b200zk_set_msm_tuning(0, 0)
+
+
 def test_prover_like_skew(gpu, oracle, table):
     """distribution "S": 70% in {0,1}, 20% < 2^16, 10% uniform -- the heavy-bucket split path"""
     pts, h, n = table
@@ -144,7 +171,7 @@ def test_all_window_sizes_and_task_splits(gpu, oracle, table, c, smax, tables):
         h = register(gpu, pts, n, fmt=0 if tables else NO_TABLES)
         assert msm(gpu, h, sc, n) == exp
         assert msm(gpu, h, sc[32 * 100:], n - 500, offset=100) == oracle.msm(pts[96 * 100:], sc[32 * 100:], n - 500)
-        for variant in range(4):
+        for variant in range(6):
             gpu.capi.check(gpu.lib().b200zk_set_msm_tuning(c | ((variant + 1) << 8), smax))
             assert msm(gpu, h, sc, n) == exp, variant
         gpu.capi.check(gpu.lib().b200zk_bases_release(h))
