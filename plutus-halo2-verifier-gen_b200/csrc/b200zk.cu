@@ -123,7 +123,7 @@ struct Ctx {
     MsmPlan last_plan{};
     // MSM workspace
     DevBuf scalars, counts, offsets, cursor, ntask, task_off, entries, task_bucket, task_start, task_len, buckets,
-        partials, len_hist, len_off, order, heavy, aff_a, aff_b, aff_pre, redS[2], redA[2], scan_tmp[2], out_mont, out_canon, stage, flag;
+        partials, len_hist, len_off, order, heavy, heavy_items, aff_a, aff_b, aff_pre, redS[2], redA[2], scan_tmp[2], out_mont, out_canon, stage, flag;
     // NTT workspace
     DevBuf ntt_data, ntt_tmp[2], small;
 };
@@ -197,9 +197,10 @@ MsmPlan msm_plan(uint64_t n, uint32_t batch, const BaseTable* tab) {
     double avg = (double)n * (precomp ? pl.W : 1) / (double)pl.nb;
     uint32_t smax = 32;
     while ((double)smax < 2.0 * avg && smax < (1u << 20)) smax <<= 1;
-    // small problems: split further so that the accumulate kernel still fills the machine
-    double entries = (double)n * pl.W * batch;
-    while (smax > 8 && entries / smax < 131072.0) smax >>= 1;
+    // a task is one thread's serial chain: never longer than 1024 additions.  (Splitting typical buckets
+    // further to "fill the machine" on small problems was measured to cost more in the collapse step
+    // than it saved in the accumulate kernel.)
+    if (smax > 1024) smax = 1024;
     if (g.tune_smax) smax = g.tune_smax;
     pl.smax = smax;
     return pl;
@@ -235,7 +236,10 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     TRY(g.len_hist.ensure(((size_t)pl.smax + 2) * 4));
     TRY(g.len_off.ensure(((size_t)pl.smax + 2) * 4));
     TRY(g.order.ensure(max_tasks * 4));
-    TRY(g.heavy.ensure((max_entries / pl.smax + 2) * 4));
+    const uint64_t hmax = max_entries / pl.smax + 2;                       // heavy buckets (split into > 1 task)
+    const uint64_t imax = hmax + max_tasks / HEAVY_CHUNK + 2;              // their work items
+    TRY(g.heavy.ensure((4 + 3 * hmax + 2 * imax) * 4));
+    TRY(g.heavy_items.ensure(imax * 192));
     TRY(g.buckets.ensure(NBt * 192));
     TRY(g.partials.ensure(max_tasks * 192));
     uint64_t m1 = (pl.nb + RED_RADIX - 1) / RED_RADIX, m2 = (m1 + RED_RADIX - 1) / RED_RADIX;
@@ -270,16 +274,22 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     uint32_t* len_hist = g.len_hist.as<uint32_t>();
     uint32_t* len_off = g.len_off.as<uint32_t>();
     uint32_t* order = g.order.as<uint32_t>();
-    uint32_t* heavy = g.heavy.as<uint32_t>();      // [0] = count, [1..] = bucket ids
+    HeavyArrays hv;
+    hv.count = g.heavy.as<uint32_t>();
+    hv.bucket = hv.count + 4;
+    hv.base = hv.bucket + hmax;
+    hv.done = hv.base + hmax;
+    hv.item_slot = hv.done + hmax;
+    hv.item_chunk = hv.item_slot + imax;
     CU(cudaMemsetAsync(len_hist, 0, ((size_t)pl.smax + 2) * 4, s));
-    CU(cudaMemsetAsync(heavy, 0, 4, s));
+    CU(cudaMemsetAsync(hv.count, 0, 16, s));
     LAUNCH(msm_task_emit_kernel, bgrid, 256, 0, s, (const uint32_t*)counts, (const uint32_t*)offsets,
            (const uint32_t*)task_off, NBt, pl.smax, g.task_bucket.as<uint32_t>(), g.task_start.as<uint32_t>(),
            g.task_len.as<uint32_t>(), len_hist);
     TRY(scan_u32(len_hist, len_off, (uint64_t)pl.smax + 1, 0, s));
     LAUNCH(msm_task_order_kernel, (unsigned)((max_tasks + 255) / 256), 256, 0, s, (const uint32_t*)g.task_len.as<uint32_t>(),
            (const uint32_t*)(task_off + NBt), pl.smax, len_off, order);
-    LAUNCH(msm_heavy_list_kernel, bgrid, 256, 0, s, (const uint32_t*)ntask, NBt, heavy, heavy + 1);
+    LAUNCH(msm_heavy_list_kernel, bgrid, 256, 0, s, (const uint32_t*)ntask, NBt, hv);
     CU(cudaMemsetAsync(buckets, 0, NBt * 192, s));
     TRY(prof_mark(1, s));
     {
@@ -309,7 +319,7 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     }
     TRY(prof_mark(2, s));
     LAUNCH(msm_collapse_kernel, (unsigned)(g.prop.multiProcessorCount * 4), 128, 0, s, (const uint32_t*)ntask,
-           (const uint32_t*)task_off, (const uint32_t*)heavy, (const uint32_t*)(heavy + 1), (const uint32_t*)partials, buckets);
+           (const uint32_t*)task_off, hv, (const uint32_t*)partials, g.heavy_items.as<uint32_t>(), buckets);
 
     // bucket reduction tree: work-efficient serial radix-16 groups while there are enough of them to fill
     // the machine, then warp-cooperative radix-32 groups (short dependency chains) for the upper levels
@@ -750,7 +760,7 @@ int32_t b200zk_shutdown(void) {
     g.coset_tables.clear();
     if (g.fixed_table) { cudaFree(g.fixed_table); g.fixed_table = nullptr; }
     DevBuf* all[] = {&g.scalars, &g.counts, &g.offsets, &g.cursor, &g.ntask, &g.task_off, &g.entries, &g.task_bucket,
-                     &g.task_start, &g.task_len, &g.buckets, &g.partials, &g.len_hist, &g.len_off, &g.order, &g.heavy, &g.aff_a, &g.aff_b, &g.aff_pre, &g.redS[0], &g.redS[1], &g.redA[0], &g.redA[1],
+                     &g.task_start, &g.task_len, &g.buckets, &g.partials, &g.len_hist, &g.len_off, &g.order, &g.heavy, &g.heavy_items, &g.aff_a, &g.aff_b, &g.aff_pre, &g.redS[0], &g.redS[1], &g.redA[0], &g.redA[1],
                      &g.scan_tmp[0], &g.scan_tmp[1], &g.out_mont, &g.out_canon, &g.stage, &g.flag, &g.ntt_data,
                      &g.ntt_tmp[0], &g.ntt_tmp[1], &g.small};
     for (DevBuf* b : all) b->release();

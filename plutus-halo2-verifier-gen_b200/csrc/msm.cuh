@@ -155,27 +155,41 @@ __device__ __forceinline__ int32_t msm_digit(const uint32_t s[9], uint32_t w, ui
 }
 
 // MODE 0: histogram.  MODE 1: scatter (cursor[] holds the running write position per bucket).
+// Lanes of a warp that hit the same bucket in the same window are merged into one atomic
+// (match.any): with uniform scalars that never happens and costs one extra instruction, with the
+// prover's 0/1 columns or constant scalars it removes the same-address serialisation entirely.
 template <int MODE>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, uint32_t fmt_mont,
                                                          MsmPlan pl, uint32_t* __restrict__ counts_or_cursor,
                                                          uint32_t* __restrict__ entries) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const bool live = i < n;
     const uint32_t b = blockIdx.y;             // batch item: its own scalar vector and bucket sets
+    const uint32_t lane = threadIdx.x & 31;
     uint32_t s[9];
-    msm_load_scalar(scalars, (uint64_t)b * n + i, fmt_mont, s);
+    if (live) msm_load_scalar(scalars, (uint64_t)b * n + i, fmt_mont, s);
+    else {
+#pragma unroll
+        for (int k = 0; k < 9; k++) s[k] = 0;
+    }
     uint32_t carry = 0;
     for (uint32_t w = 0; w < pl.W; w++) {
         int32_t d = msm_digit(s, w, pl.c, carry);
-        if (d == 0) continue;
         uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
         // with precomputed rows every window feeds the same bucket set and the entry names the row
         uint32_t g = pl.precomp ? b * pl.nb + mag - 1 : (b * pl.W + w) * pl.nb + mag - 1;
-        if (MODE == 0) atomicAdd(&counts_or_cursor[g], 1u);
-        else {
-            uint32_t pos = atomicAdd(&counts_or_cursor[g], 1u);
-            uint32_t idx = pl.precomp ? (uint32_t)(w * pl.row_stride + i) : (uint32_t)i;
-            entries[pos] = idx | (d < 0 ? 0x80000000u : 0u);
+        bool valid = live && d != 0;
+        uint32_t key = valid ? g : (0xffffffe0u + lane);          // invalid lanes get private keys
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
+        uint32_t leader = __ffs(peers) - 1, cnt = __popc(peers), rank = __popc(peers & ((1u << lane) - 1));
+        uint32_t pos = 0;
+        if (valid && lane == leader) pos = atomicAdd(&counts_or_cursor[g], cnt);
+        if (MODE == 1) {
+            pos = __shfl_sync(0xffffffffu, pos, leader);
+            if (valid) {
+                uint32_t idx = pl.precomp ? (uint32_t)(w * pl.row_stride + i) : (uint32_t)i;
+                entries[pos + rank] = idx | (d < 0 ? 0x80000000u : 0u);
+            }
         }
     }
 }
@@ -337,44 +351,98 @@ __global__ void __launch_bounds__(128, 3) msm_accumulate_affine_kernel_r168(MSM_
 }
 
 // ---------------------------------------------------------------------------------------
-// 6. collapse split buckets: heavy_list holds the buckets that were split into several tasks
-//    (appended by msm_heavy_list_kernel); a fixed grid of warps walks the list, lanes stride over
-//    the bucket's task partials and a shared-memory tree folds the 32 lane sums.
+// 6. collapse split buckets.  A bucket that was split into nt tasks has nt XYZZ partials to fold.
+//    The list kernel turns every such bucket into ceil(nt / 1024) work items; a fixed grid of warps
+//    walks the items: lanes stride over <= 1024 partials (<= 32 additions each) and a shared-memory
+//    tree folds the 32 lane sums.  A bucket with several items (a 0/1 column puts a third of all
+//    points into one bucket) is finished by whichever warp completes its last item: it folds the
+//    item results the same way.  No host round trip, no level loop.
 // ---------------------------------------------------------------------------------------
-__global__ void msm_heavy_list_kernel(const uint32_t* __restrict__ ntask, uint64_t nbuckets, uint32_t* heavy_count,
-                                      uint32_t* heavy_list) {
+constexpr uint32_t HEAVY_CHUNK = 1024;
+struct HeavyArrays {
+    uint32_t* count;      // [0] heavy buckets, [1] work items
+    uint32_t* bucket;     // per heavy slot: bucket id
+    uint32_t* base;       // per heavy slot: first work item
+    uint32_t* done;       // per heavy slot: finished items
+    uint32_t* item_slot;  // per work item: heavy slot
+    uint32_t* item_chunk; // per work item: chunk number
+};
+__global__ void msm_heavy_list_kernel(const uint32_t* __restrict__ ntask, uint64_t nbuckets, HeavyArrays hv) {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nbuckets) return;
-    if (ntask[g] > 1) heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)g;
+    uint32_t nt = ntask[g];
+    if (nt <= 1) return;
+    uint32_t nch = (nt + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
+    uint32_t hs = atomicAdd(&hv.count[0], 1u);
+    uint32_t base = atomicAdd(&hv.count[1], nch);
+    hv.bucket[hs] = (uint32_t)g;
+    hv.base[hs] = base;
+    hv.done[hs] = 0;
+    for (uint32_t j = 0; j < nch; j++) { hv.item_slot[base + j] = hs; hv.item_chunk[base + j] = j; }
 }
-__global__ void __launch_bounds__(128) msm_collapse_kernel(const uint32_t* __restrict__ ntask, const uint32_t* __restrict__ task_off,
-                                                           const uint32_t* __restrict__ heavy_count,
-                                                           const uint32_t* __restrict__ heavy_list,
-                                                           const uint32_t* __restrict__ partials,
-                                                           uint32_t* __restrict__ buckets) {
-    __shared__ uint32_t sm[4 * 16 * 48];  // per warp: 16 XYZZ points for the lane tree
-    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t nheavy = *heavy_count;
-    uint32_t* my = sm + wid * 16 * 48;
-    for (uint32_t h = blockIdx.x * 4 + wid; h < nheavy; h += gridDim.x * 4) {
-        uint32_t g = heavy_list[h];
-        uint32_t nt = ntask[g], t0 = task_off[g];
-        G1Xyzz acc;
-        xyzz_set_inf(acc);
-        for (uint32_t k = lane; k < nt; k += 32) {
-            G1Xyzz p = xyzz_ld(partials, t0 + k);
+__device__ __forceinline__ G1Xyzz xyzz_ld_cg(const uint32_t* arr, uint64_t i) {
+    const uint4* q = reinterpret_cast<const uint4*>(arr + 48 * i);
+    uint32_t v[48];
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        uint4 t = __ldcg(q + k);
+        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+    }
+    G1Xyzz a;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { a.x.l[k] = v[k]; a.y.l[k] = v[12 + k]; a.zz.l[k] = v[24 + k]; a.zzz.l[k] = v[36 + k]; }
+    return a;
+}
+// sum of src[first .. first+count) over the warp: strided lane sums, then a 5-step tree through smem
+__device__ __forceinline__ G1Xyzz warp_fold(const uint32_t* __restrict__ src, uint64_t first, uint32_t count, uint32_t* my,
+                                            uint32_t lane, bool cg) {
+    G1Xyzz acc;
+    xyzz_set_inf(acc);
+    for (uint32_t k = lane; k < count; k += 32) {
+        G1Xyzz p = cg ? xyzz_ld_cg(src, first + k) : xyzz_ld(src, first + k);
+        xyzz_add_ni(acc, p);
+    }
+    for (int half = 16; half >= 1; half >>= 1) {
+        if (lane >= half && lane < 2 * half) xyzz_st(my, lane - half, acc);
+        __syncwarp();
+        if (lane < half) {
+            G1Xyzz p = xyzz_ld(my, lane);
             xyzz_add_ni(acc, p);
         }
-        for (int half = 16; half >= 1; half >>= 1) {
-            if (lane >= half && lane < 2 * half) xyzz_st(my, lane - half, acc);
-            __syncwarp();
-            if (lane < half) {
-                G1Xyzz p = xyzz_ld(my, lane);
-                xyzz_add_ni(acc, p);
-            }
-            __syncwarp();
+        __syncwarp();
+    }
+    return acc;
+}
+__global__ void __launch_bounds__(128) msm_collapse_kernel(const uint32_t* __restrict__ ntask, const uint32_t* __restrict__ task_off,
+                                                           HeavyArrays hv, const uint32_t* __restrict__ partials,
+                                                           uint32_t* __restrict__ item_out, uint32_t* __restrict__ buckets) {
+    __shared__ uint32_t sm[4 * 16 * 48];  // per warp: 16 XYZZ points for the lane tree
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t nitems = hv.count[1];
+    uint32_t* my = sm + wid * 16 * 48;
+    for (uint32_t it = blockIdx.x * 4 + wid; it < nitems; it += gridDim.x * 4) {
+        uint32_t hs = hv.item_slot[it], j = hv.item_chunk[it];
+        uint32_t g = hv.bucket[hs];
+        uint32_t nt = ntask[g], t0 = task_off[g];
+        uint32_t nch = (nt + HEAVY_CHUNK - 1) / HEAVY_CHUNK;
+        uint32_t lo = j * HEAVY_CHUNK, cnt = min(HEAVY_CHUNK, nt - lo);
+        G1Xyzz acc = warp_fold(partials, (uint64_t)t0 + lo, cnt, my, lane, false);
+        if (nch == 1) {
+            if (lane == 0) xyzz_st(buckets, g, acc);
+            continue;
         }
-        if (lane == 0) xyzz_st(buckets, g, acc);
+        uint32_t last = 0;
+        if (lane == 0) {
+            xyzz_st(item_out, it, acc);
+            __threadfence();
+            last = (atomicAdd(&hv.done[hs], 1u) == nch - 1) ? 1u : 0u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {                                        // every item of this bucket is in item_out
+            __threadfence();
+            G1Xyzz tot = warp_fold(item_out, hv.base[hs], nch, my, lane, true);
+            if (lane == 0) xyzz_st(buckets, g, tot);
+        }
     }
 }
 
