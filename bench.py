@@ -116,6 +116,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic(fname, n_kernels):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the
+    same command (profiles/), summed over the launches that make up one step of that kernel; None if absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", fname)))
+        ks = d["kernels"][:n_kernels]
+        return sum(k["traffic_bytes"] for k in ks) if len(ks) == n_kernels else None
+    except Exception:
+        return None
+
+
 def load_oracle():
     so = os.path.join(ROOT, "oracle", "liboracle.so")
     if not os.path.exists(so):
@@ -349,7 +360,10 @@ def main():
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved / 1e12,
                          "peak": imad_peak / 1e12, "unit": "Tlimb-MAC/s", "frac": achieved / imad_peak if imad_peak else None,
-                         "traffic": None,
+                         "traffic": ncu_traffic("r01_ncu_msm_accumulate_2p24.json", 1) if (args.log_n == 24 and world == 1) else None,
+                         "traffic_note": "bytes per launch of the accumulate kernel (ncu capture of this command, profiles/); "
+                                         "algorithmic bytes = (96 B base + 4 B entry) x points x rows = %.1f GB"
+                                         % (100.0 * n_local * (prof.get("windows") or 0) / 1e9),
                          "note": "algorithmic work = %d limb-MACs/point x %d points per launch / accumulate-kernel time "
                                  "(CUDA events on the launching stream, last timed step, max over ranks); peak = IMAD.WIDE.U32 "
                                  "micro-benchmark measured in this run; window bits actually used: %s"
@@ -417,7 +431,7 @@ def bench_ntt(zk, lib, torch, np, args, stream, imad_peak):
         "e2e": {"value": n / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n,
                 "ms_per_step": e2e_s * 1e3},
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                     "traffic": None,
+                     "traffic": ncu_traffic("r01_ncu_ntt_pass_2p22.json", 2) if log_n == 22 else None,
                      "imad": {"achieved_tlmac_s": lmacs / (ms * 1e-3) / 1e12, "peak_tlmac_s": imad_peak / 1e12,
                               "frac": (lmacs / (ms * 1e-3)) / imad_peak if imad_peak else None},
                      "binding": "imad" if t_imad > t_hbm else "hbm", "frac_of_binding_bound": t_bound / (ms * 1e-3),

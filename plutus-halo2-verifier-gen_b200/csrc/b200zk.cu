@@ -262,12 +262,13 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     CU(cudaMemsetAsync(counts, 0, (NBt + 1) * 4, s));
     CU(cudaMemsetAsync(ntask, 0, (NBt + 1) * 4, s));
     dim3 dgrid((unsigned)((n + 255) / 256), batch);
-    LAUNCH(msm_digits_kernel<0>, dgrid, 256, 0, s, d_scalars, n, scalar_fmt == B200ZK_FMT_MONT ? 1u : 0u, pl, counts,
-           (uint32_t*)nullptr);
+    const uint32_t fmt_mont = scalar_fmt == B200ZK_FMT_MONT ? 1u : 0u;
+    // (A two-pass sort -- coarse bins of 2048 buckets staged through shared memory, then one CTA per bin --
+    // was built and measured at 2^24: 11.0 ms against 7.9 ms for this one-pass histogram + scatter; removed.)
+    LAUNCH(msm_digits_kernel<0>, dgrid, 256, 0, s, d_scalars, n, fmt_mont, pl, counts, (uint32_t*)nullptr);
     TRY(scan_u32(counts, offsets, NBt + 1, 0, s));
     CU(cudaMemcpyAsync(cursor, offsets, (NBt + 1) * 4, cudaMemcpyDeviceToDevice, s));
-    LAUNCH(msm_digits_kernel<1>, dgrid, 256, 0, s, d_scalars, n, scalar_fmt == B200ZK_FMT_MONT ? 1u : 0u, pl, cursor,
-           entries);
+    LAUNCH(msm_digits_kernel<1>, dgrid, 256, 0, s, d_scalars, n, fmt_mont, pl, cursor, entries);
     unsigned bgrid = (unsigned)((NBt + 255) / 256);
     LAUNCH(msm_task_count_kernel, bgrid, 256, 0, s, (const uint32_t*)counts, NBt, pl.smax, ntask);
     TRY(scan_u32(ntask, task_off, NBt + 1, 0, s));

@@ -348,3 +348,26 @@ def test_sharded_partials_emulated_on_one_gpu(gpu, oracle):
     assert bytes(out.cpu().numpy()) == oracle.msm(pts[:96 * e0], sc[:32 * e0], e0)
     for h in handles:
         gpu.capi.check(gpu.lib().b200zk_bases_release(h))
+
+
+@pytest.mark.parametrize("dist", ["uniform", "prover_like", "constant"])
+def test_large_input_sort_paths(gpu, oracle, dist):
+    """2^19 points: large enough for the two-pass counting sort (uniform) and for its device-side
+    fall-back to the one-pass sort on skewed inputs (0/1 columns, constant scalars)."""
+    import numpy as np
+    n = 1 << 19
+    pts = oracle.synth_bases(0xB700, 0, n)
+    h = register(gpu, pts, n)
+    uni = np.frombuffer(oracle.synth_scalars(61, 0, n), dtype=np.uint64).reshape(n, 4).copy()
+    if dist == "prover_like":
+        rng = np.random.default_rng(5)
+        u = rng.random(n)
+        small = u < 0.9
+        uni[small, 1:] = 0
+        uni[small, 0] = np.where(u[small] < 0.7, rng.integers(0, 2, small.sum(), dtype=np.uint64),
+                                 rng.integers(0, 1 << 16, small.sum(), dtype=np.uint64))
+    elif dist == "constant":
+        uni[:] = np.frombuffer((R - 1).to_bytes(32, "little"), dtype=np.uint64)
+    sc = uni.tobytes()
+    assert msm(gpu, h, sc, n) == oracle.msm(pts, sc, n)
+    gpu.capi.check(gpu.lib().b200zk_bases_release(h))

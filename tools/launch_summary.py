@@ -33,6 +33,9 @@ def main(path):
         j = i
         while j > 0 and "msm_digits_kernel<0>" not in seq[j][1]:
             j -= 1
+        while j > 0 and ("msm_coarse" in seq[j - 1][1] or "msm_fine" in seq[j - 1][1] or
+                         ("scan_tile" in seq[j - 1][1] and j > 1 and "msm_coarse" in seq[j - 2][1])):
+            j -= 1
         k = i
         while k < len(seq) and "msm_combine" not in seq[k][1]:
             k += 1
