@@ -69,3 +69,48 @@ def test_batched_verifier_full_shape(gpu, oracle):
     out = C.create_string_buffer(96)
     gpu.capi.check(gpu.lib().b200zk_msm_g1_adhoc(gpu.capi.addr(pts), 0, gpu.capi.addr(sc), 0, n, gpu.capi.addr(out)))
     assert out.raw == oracle.msm(pts, sc, n)
+
+
+def test_kzg_coefficient_and_lagrange_commitments_agree(gpu, oracle, pyref):
+    """The identity the prover relies on when it mixes commit and commit_lagrange: with g_i = s^i G and
+    g_lagrange_i = L_i(s) G (what ParamsKZG::unsafe_setup produces, /root/reference/src/kzg_params.rs:43),
+    commit(coefficients) == commit_lagrange(NTT(coefficients)) == p(s) G.  Ties the CUDA MSM and the
+    CUDA NTT together through a value neither of them computes."""
+    k = 7
+    n = 1 << k
+    s = 0x1234567890ABCDEF1234567890ABCDEF % R
+    G = oracle.g1_generator()
+    omega = pyref.omega(k)
+    powers = [pow(s, i, R) for i in range(n)]
+    # L_i(s) = (s^n - 1)/n * w^i / (s - w^i)
+    zn = (pow(s, n, R) - 1) * pyref.fr_inv(n) % R
+    lag = [zn * pow(omega, i, R) % R * pyref.fr_inv((s - pow(omega, i, R)) % R) % R for i in range(n)]
+    g = b"".join(oracle.g1_mul(G, fr(x)) for x in powers)
+    gl = b"".join(oracle.g1_mul(G, fr(x)) for x in lag)
+    params = gpu.host.ParamsKZG(k, g, gl)
+    dom = gpu.host.EvaluationDomain(4, k)
+    coeffs = oracle.synth_scalars(77, 0, n)
+    evals = dom.coeff_to_lagrange(coeffs)
+    c1 = gpu.host.KZGCommitmentScheme.commit(params, coeffs)
+    c2 = gpu.host.KZGCommitmentScheme.commit_lagrange(params, evals)
+    ps = sum(int.from_bytes(coeffs[32 * i:32 * i + 32], "little") * powers[i] for i in range(n)) % R
+    assert c1 == c2 == oracle.g1_mul(G, fr(ps))
+    # and the verifier-side shape: e(pi, [s]G2) == e(right, G2) holds iff s*left == right in G1 when s is known
+    # (opening of p at z with quotient q = (p - p(z)) / (X - z)): commit(p) - p(z) G + z*commit(q) == s*commit(q)
+    z = 0xDEADBEEF
+    cz = [int.from_bytes(coeffs[32 * i:32 * i + 32], "little") for i in range(n)]
+    pz = 0
+    q = [0] * n
+    for i in range(n - 1, -1, -1):        # synthetic division by (X - z)
+        q[i] = pz
+        pz = (pz * z + cz[i]) % R
+    qb = b"".join(fr(x) for x in q)
+    pi = gpu.host.KZGCommitmentScheme.commit(params, qb)
+    dual = gpu.host.DualMSM()
+    dual.append_left(1, pi)
+    dual.append_right(1, c1)
+    dual.append_right(-pz, G)
+    dual.append_right(z, pi)
+    left, right = dual.eval()
+    assert oracle.g1_mul(left, fr(s)) == right
+    params.release()
