@@ -84,8 +84,58 @@ struct MulCall {
     static __device__ __forceinline__ Fp mul(const Fp& a, const Fp& b) { return fp_mul_call(a, b); }
 };
 __device__ __forceinline__ Fp fp_mul_ni(const Fp& a, const Fp& b) { return fp_mul_call(a, b); }
-__device__ __forceinline__ void xyzz_add_ni(G1Xyzz& acc, const G1Xyzz& q) { xyzz_add_t<MulCall>(acc, q); }
-__device__ __forceinline__ void xyzz_dbl_ni(G1Xyzz& acc) { xyzz_dbl_t<MulCall>(acc); }
+// The tail kernels (collapse, bucket-reduce tree, combine, partial sums) run few threads, so what counts
+// there is the latency of ONE point addition.  They all go through the two functions below: operands and
+// result in memory (any address space), the 14 (9) field products inlined inside so that independent
+// products overlap and no call/spill traffic sits between them.  One copy of that code in the program.
+__device__ __forceinline__ G1Xyzz xyzz_ld_gen(const uint32_t* p) {
+    G1Xyzz a;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { a.x.l[k] = p[k]; a.y.l[k] = p[12 + k]; a.zz.l[k] = p[24 + k]; a.zzz.l[k] = p[36 + k]; }
+    return a;
+}
+__device__ __forceinline__ void xyzz_st_gen(uint32_t* p, const G1Xyzz& a) {
+#pragma unroll
+    for (int k = 0; k < 12; k++) { p[k] = a.x.l[k]; p[12 + k] = a.y.l[k]; p[24 + k] = a.zz.l[k]; p[36 + k] = a.zzz.l[k]; }
+}
+__device__ __noinline__ void xyzz_dbl_mem(uint32_t* acc) {
+    G1Xyzz a = xyzz_ld_gen(acc);
+    xyzz_dbl_t<MulInline>(a);
+    xyzz_st_gen(acc, a);
+}
+__device__ __noinline__ void xyzz_add_mem(uint32_t* acc, const uint32_t* q) {
+    G1Xyzz a = xyzz_ld_gen(acc), b = xyzz_ld_gen(q);
+    if (xyzz_is_inf(b)) return;
+    if (xyzz_is_inf(a)) { xyzz_st_gen(acc, b); return; }
+    Fp u1 = fe_mul(a.x, b.zz), u2 = fe_mul(b.x, a.zz), s1 = fe_mul(a.y, b.zzz), s2 = fe_mul(b.y, a.zzz);
+    Fp p = fe_sub(u2, u1), r = fe_sub(s2, s1);
+    if (fe_is_zero(p)) {
+        if (fe_is_zero(r)) xyzz_dbl_mem(acc);               // same point (acc is still unchanged in memory)
+        else { xyzz_set_inf(a); xyzz_st_gen(acc, a); }       // opposite points
+        return;
+    }
+    Fp pp = fe_mul(p, p);
+    Fp ppp = fe_mul(p, pp), qq = fe_mul(u1, pp), zz = fe_mul(a.zz, b.zz), zzz = fe_mul(a.zzz, b.zzz);
+    Fp x3 = fe_sub(fe_sub(fe_sub(fe_mul(r, r), ppp), qq), qq);
+    a.y = fe_sub(fe_mul(r, fe_sub(qq, x3)), fe_mul(s1, ppp));
+    a.x = x3;
+    a.zz = fe_mul(zz, pp);
+    a.zzz = fe_mul(zzz, ppp);
+    xyzz_st_gen(acc, a);
+}
+__device__ __forceinline__ void xyzz_add_ni(G1Xyzz& acc, const G1Xyzz& q) {
+    uint32_t ta[48], tq[48];
+    xyzz_st_gen(ta, acc);
+    xyzz_st_gen(tq, q);
+    xyzz_add_mem(ta, tq);
+    acc = xyzz_ld_gen(ta);
+}
+__device__ __forceinline__ void xyzz_dbl_ni(G1Xyzz& acc) {
+    uint32_t ta[48];
+    xyzz_st_gen(ta, acc);
+    xyzz_dbl_mem(ta);
+    acc = xyzz_ld_gen(ta);
+}
 // binary-GCD inversion, out of line (one call site per kernel)
 __device__ __noinline__ Fp fp_inv_ni(Fp a) { return fe_inv_gcd(a); }
 __device__ __forceinline__ G1Affine xyzz_to_affine_ni(const G1Xyzz& a) {
