@@ -5,18 +5,28 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 HOSTCXX ?= /usr/bin/g++
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -ccbin $(HOSTCXX) \
            -Iinclude -I$(PKG)/csrc
-SRCS := $(PKG)/csrc/b200zk.cu
-HDRS := $(wildcard $(PKG)/csrc/*.cuh) include/b200zk.h
+SRCS := $(PKG)/csrc/b200zk.cu $(PKG)/csrc/b200zk_ext.cu
+OBJS := $(SRCS:$(PKG)/csrc/%.cu=build/%.o)
+HDRS := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.hpp) include/b200zk.h
 
-all: $(PKG)/libb200zk.so oracle
+all:
+	$(MAKE) -j2 lib
+	$(MAKE) oracle
 
-$(PKG)/libb200zk.so: $(SRCS) $(HDRS)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRCS) -lcudart
+lib: $(PKG)/libb200zk.so
+
+# two translation units (MSM + NTT + context; polynomial side + SRS + decompression) compiled side by side
+build/%.o: $(PKG)/csrc/%.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+
+$(PKG)/libb200zk.so: $(OBJS)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(OBJS) -lcudart
 
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -f $(PKG)/libb200zk.so
+	rm -rf $(PKG)/libb200zk.so build
 	$(MAKE) -C oracle clean
-.PHONY: all oracle clean
+.PHONY: all lib oracle clean

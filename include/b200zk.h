@@ -144,6 +144,78 @@ int32_t b200zk_ntt_fr_dev(void *d_data, uint32_t batch, uint32_t log_n, const ui
  * carries (/root/reference/aiken-verifier/aiken_halo2/lib/transcript.ak:62-83,121-156).  Host-side byte logic. */
 int32_t b200zk_g1_compress(const uint8_t affine[96], uint8_t out[48]);
 
+/* =============================================================================================
+ * Components next to the hot path: columns stay resident in HBM between the NTTs and
+ * the commitments.  All Fr vectors below are DEVICE arrays of 32-byte elements in Montgomery form (the
+ * in-memory form of midnight_curves::Fq; b200zk_fr_convert_dev converts); host scalars are canonical.
+ * ============================================================================================= */
+
+/* ---- device memory, for a shim that does not link the CUDA runtime ------------------------------ */
+int32_t b200zk_dev_alloc(void **out, size_t bytes);
+int32_t b200zk_dev_free(void *p);
+int32_t b200zk_dev_upload(void *d_dst, const void *src, size_t bytes);   /* synchronous */
+int32_t b200zk_dev_download(void *dst, const void *d_src, size_t bytes); /* synchronous, after all streams */
+
+/* ---- batched G1 decompression: the front end of (batched) verification ----------------------------
+ * Every proof carries its commitments as 48-byte compressed points
+ * (/root/reference/aiken-verifier/aiken_halo2/lib/transcript.ak:62-83; y = (x^3+4)^((p+1)/4),
+ * /root/reference/plinth-verifier/plutus-halo2/src/Plutus/Crypto/Halo2/CompressUncompress.hs:70-100).
+ * status[i]: 0 ok, 1 not a compressed encoding, 2 bad infinity encoding, 3 x >= p, 4 x not on the curve.
+ * The host variant returns B200ZK_ERR_BAD_POINT if any status is non-zero (status may be NULL);
+ * rejected points are written as (0,0).  No subgroup check, like the in-tree uncompress.             */
+int32_t b200zk_g1_decompress_batch(const uint8_t *compressed, uint64_t n, uint8_t *out_affine, uint32_t *status);
+int32_t b200zk_g1_decompress_dev(const void *d_compressed, uint64_t n, void *d_out_mont, void *d_out_canon, void *d_status,
+                                 void *stream);
+
+/* ---- SRS generation (ParamsKZG::unsafe_setup behind /root/reference/src/kzg_params.rs:33-80) -------
+ * g[i] = s^i * G and g_lagrange[i] = L_i(s) * G, L_i the Lagrange basis of the 2^k-th roots of unity
+ * generated by omega; both written as packed Montgomery affine points (96 bytes = blst_p1_affine), ready
+ * for b200zk_bases_register_dev.  Either output may be NULL.  Fixed-base multiplication: 32 byte windows. */
+int32_t b200zk_srs_generate_dev(const uint8_t s[32], uint32_t k, const uint8_t omega[32], void *d_g_mont,
+                                void *d_g_lagrange_mont, void *stream);
+/* out[i] = scalars[i] * G */
+int32_t b200zk_g1_fixed_mul_dev(const void *d_scalars, uint32_t scalar_fmt, uint64_t n, void *d_out_mont, void *stream);
+/* packed Montgomery affine points in HBM -> canonical wire format on the host */
+int32_t b200zk_g1_export_dev(const void *d_points_mont, uint64_t n, uint8_t *out_affine);
+
+/* ---- Fr vectors: the polynomial side of multi_open and of the permutation / lookup arguments ------- */
+int32_t b200zk_fr_convert_dev(const void *d_in, void *d_out, uint64_t n, uint32_t to_mont, void *stream);
+/* op 0: out = a*b, 1: a+b, 2: a-b, 3: a*scalar, 4: out += a*b   (in place allowed) */
+int32_t b200zk_fr_pointwise_dev(uint32_t op, const void *d_a, const void *d_b, const uint8_t scalar[32], void *d_out,
+                                uint64_t n, void *stream);
+/* out = sum_k coeffs[k] * polys[k]: the x1 / x2 / x4 linear combinations of multi_open
+ * (/root/reference/src/plutus_gen/extraction/pcs/kzg.rs:55-79); d_polys is a HOST array of device pointers */
+int32_t b200zk_fr_lincomb_dev(const void *const *d_polys, const uint8_t *coeffs, uint32_t count, void *d_out, uint64_t n,
+                              void *stream);
+/* elementwise inverse, zeros stay zero (halo2 batch_invert); in place allowed */
+int32_t b200zk_fr_batch_invert_dev(const void *d_in, void *d_out, uint64_t n, void *stream);
+/* out[i] = init * prod_{j<i} in[j] (exclusive) or prod_{j<=i} (inclusive): the grand products
+ * z(omega X) = z(X) * num / den of the permutation and lookup arguments; init NULL = 1; in place allowed */
+int32_t b200zk_fr_running_product_dev(const void *d_in, void *d_out, uint64_t n, const uint8_t init[32], uint32_t inclusive,
+                                      void *stream);
+/* One sweep: eval = p(z) and quot = (p(X) - p(z)) / (X - z) (n-1 coefficients) for p of n coefficients.
+ * Either output may be NULL.  d_quot must not overlap d_coeffs.                                        */
+int32_t b200zk_fr_kate_div_dev(const void *d_coeffs, uint64_t n, const uint8_t z[32], void *d_quot, void *d_eval, void *stream);
+
+/* ---- gate programs: evaluation of the quotient's numerator over the extended coset domain ------------
+ * (upstream plonk evaluation of h(X); consumed as the vanishing commitments,
+ * /root/reference/src/plutus_gen/extraction/data/extraction_steps/proof.rs:76-80; the gate expressions are the ones the
+ * reference walks at /root/reference/src/plutus_gen/extraction/mod.rs:81-102).
+ * A program is a register machine of n_instr instructions of 4 x u32 { op | dst << 8, src a, src b, src c }:
+ *   src = kind << 28 | payload;  kind 0: consts[payload]; 1: register[payload];
+ *                                kind 2: columns[payload >> 12] at row + rotations[payload & 0xfff] * 2^(log_ext - log_n)
+ *   op 0 add, 1 sub, 2 mul, 3 neg(a), 4 double(a), 5 square(a), 6 muladd a*b + c, 7 mov(a); at most 48 registers.
+ * One launch evaluates the program at every row of the 2^log_ext domain; the last destination register, times
+ * t_inv[row mod 2^log_period] when t_inv is given (1/(X^n - 1) on the coset), is written (or added) to out. */
+#define B200ZK_GATE_MAX_REGS 48u
+int32_t b200zk_gate_program_create(const uint32_t *program, uint32_t n_instr, const uint8_t *consts, uint32_t n_consts,
+                                   const int32_t *rotations, uint32_t n_rotations, const uint8_t *t_inv, uint32_t log_period,
+                                   uint32_t n_columns, uint32_t log_n, uint32_t log_ext, uint64_t *out_handle);
+int32_t b200zk_gate_program_set_const(uint64_t handle, uint32_t index, const uint8_t value[32]); /* challenges */
+int32_t b200zk_gate_program_run_dev(uint64_t handle, const void *const *d_columns, void *d_out, uint32_t accumulate,
+                                    void *stream);
+int32_t b200zk_gate_program_release(uint64_t handle);
+
 /* ---- synthetic inputs and self-test (bench / tests) ------------------------------------------
  * bases P_i = a_i*G with a_i = splitmix64(seed + start + i), written as packed Montgomery affine. */
 int32_t b200zk_g1_synth_bases_dev(uint64_t seed, uint64_t start, uint64_t n, void *d_out_mont, void *stream);

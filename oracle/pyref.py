@@ -368,3 +368,143 @@ def synth_base_dlog(seed: int, i: int) -> int:
     """Discrete log a_i of synthetic base i: P_i = a_i * G, a_i = SplitMix64(seed + i)
     (never 0 for the seeds used)."""
     return splitmix64((seed + i) & 0xFFFFFFFFFFFFFFFF)
+
+
+# --------------------------------------------------------------------------- polynomial side (SURVEY.md 8f)
+# Checker for the Fr vector kernels next to the hot path.  Values are Python ints mod r.
+def poly_eval(coeffs, z: int) -> int:
+    """p(z) by Horner's rule (the evals the prover writes, extraction_steps/proof.rs:82-143)."""
+    acc = 0
+    for c in reversed(coeffs):
+        acc = (acc * z + c) % R_MOD
+    return acc
+
+
+def kate_div(coeffs, z: int):
+    """Synthetic division: (q, p(z)) with p(X) - p(z) = q(X) (X - z); the witness polynomials of the
+    KZG multi-open (src/plutus_gen/extraction/pcs/kzg.rs:55-79; verifier twin halo2_kzg.ak:46-171)."""
+    n = len(coeffs)
+    if n == 0:
+        return [], 0
+    q = [0] * (n - 1)
+    s = 0
+    for i in range(n - 1, -1, -1):
+        s = (s * z + coeffs[i]) % R_MOD
+        if i:
+            q[i - 1] = s
+    return q, s
+
+
+def running_product(v, init: int = 1, inclusive: bool = False):
+    """z_0 = init, z_{i+1} = z_i * v_i: the grand-product columns of the permutation and lookup
+    arguments (extraction_steps/permutation.rs)."""
+    out, acc = [], init % R_MOD
+    for x in v:
+        nxt = acc * x % R_MOD
+        out.append(nxt if inclusive else acc)
+        acc = nxt
+    return out
+
+
+def batch_invert(v):
+    """Elementwise inverse; zeros stay zero (halo2's batch_invert convention)."""
+    return [fr_inv(x) if x % R_MOD else 0 for x in v]
+
+
+def lincomb(polys, coeffs):
+    n = len(polys[0]) if polys else 0
+    return [sum(c * p[i] for c, p in zip(coeffs, polys)) % R_MOD for i in range(n)]
+
+
+def vanishing_inverse_on_coset(g_coset: int, k: int, ext_k: int):
+    """1 / (X^n - 1) at X = g * w_ext^j: only 2^(ext_k - k) distinct values, because w_ext^n has that
+    order (the division by the vanishing polynomial of the quotient, docs 'Vanishing')."""
+    n = 1 << k
+    w_ext = omega(ext_k)
+    return [fr_inv((pow(g_coset * pow(w_ext, j, R_MOD) % R_MOD, n, R_MOD) - 1) % R_MOD) for j in range(1 << (ext_k - k))]
+
+
+GATE_OPS = {"add": 0, "sub": 1, "mul": 2, "neg": 3, "double": 4, "square": 5, "muladd": 6, "mov": 7}
+
+
+def gate_const(i):
+    return (0 << 28) | i
+
+
+def gate_reg(i):
+    return (1 << 28) | i
+
+
+def gate_col(col, rot_idx):
+    return (2 << 28) | (col << 12) | rot_idx
+
+
+def gate_eval(program, consts, rotations, columns, log_n: int, log_ext: int, t_inv=None):
+    """Reference evaluation of a gate program (include/b200zk.h, b200zk_gate_program_*) at every row
+    of the extended domain: the numerator of the quotient h(X) walked gate by gate as the reference
+    walks the same expressions (src/plutus_gen/extraction/mod.rs:81-102), then divided by X^n - 1.
+    program: list of (op, dst, a, b, c) with encoded sources."""
+    n_ext = 1 << log_ext
+    scale = 1 << (log_ext - log_n)
+    out = []
+    for row in range(n_ext):
+        regs = {}
+
+        def src(s):
+            kind, pay = s >> 28, s & 0x0FFFFFFF
+            if kind == 0:
+                return consts[pay] % R_MOD
+            if kind == 1:
+                return regs[pay]
+            return columns[pay >> 12][(row + rotations[pay & 0xFFF] * scale) % n_ext]
+
+        last = None
+        for (op, dst, a, b, c) in program:
+            x = src(a)
+            if op == 0:
+                r = x + src(b)
+            elif op == 1:
+                r = x - src(b)
+            elif op == 2:
+                r = x * src(b)
+            elif op == 3:
+                r = -x
+            elif op == 4:
+                r = 2 * x
+            elif op == 5:
+                r = x * x
+            elif op == 6:
+                r = x * src(b) + src(c)
+            else:
+                r = x
+            regs[dst] = r % R_MOD
+            last = dst
+        v = regs[last] if last is not None else 0
+        if t_inv is not None:
+            v = v * t_inv[row % len(t_inv)] % R_MOD
+        out.append(v)
+    return out
+
+
+def gate_program_words(program):
+    """4 x u32 per instruction, the C-ABI encoding."""
+    words = []
+    for (op, dst, a, b, c) in program:
+        words += [op | (dst << 8), a, b, c]
+    return words
+
+
+# --------------------------------------------------------------------------- SRS (SURVEY.md 8f row 2)
+def srs_scalars(s: int, k: int):
+    """Discrete logs of ParamsKZG::unsafe_setup's two tables (src/kzg_params.rs:33-80 caches them):
+    g[i] = s^i G;  g_lagrange[i] = L_i(s) G with L_i(s) = w^i (s^n - 1) / (n (s - w^i))."""
+    n = 1 << k
+    w = omega(k)
+    mono = [pow(s, i, R_MOD) for i in range(n)]
+    c = (pow(s, n, R_MOD) - 1) * fr_inv(n) % R_MOD
+    lag = []
+    wi = 1
+    for _ in range(n):
+        lag.append(wi * c % R_MOD * fr_inv((s - wi) % R_MOD) % R_MOD)
+        wi = wi * w % R_MOD
+    return mono, lag

@@ -61,6 +61,26 @@ SIGNATURES = {
     "b200zk_ntt_fr_batch": (C.c_int32, [_u8p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, _u8p]),
     "b200zk_ntt_fr_dev": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, _u8p, C.c_void_p]),
     "b200zk_g1_compress": (C.c_int32, [_u8p, _u8p]),
+    "b200zk_dev_alloc": (C.c_int32, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "b200zk_dev_free": (C.c_int32, [C.c_void_p]),
+    "b200zk_dev_upload": (C.c_int32, [C.c_void_p, _u8p, C.c_size_t]),
+    "b200zk_dev_download": (C.c_int32, [_u8p, C.c_void_p, C.c_size_t]),
+    "b200zk_g1_decompress_batch": (C.c_int32, [_u8p, C.c_uint64, _u8p, C.c_void_p]),
+    "b200zk_g1_decompress_dev": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200zk_srs_generate_dev": (C.c_int32, [_u8p, C.c_uint32, _u8p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200zk_g1_fixed_mul_dev": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "b200zk_g1_export_dev": (C.c_int32, [C.c_void_p, C.c_uint64, _u8p]),
+    "b200zk_fr_convert_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "b200zk_fr_pointwise_dev": (C.c_int32, [C.c_uint32, C.c_void_p, C.c_void_p, _u8p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "b200zk_fr_lincomb_dev": (C.c_int32, [C.c_void_p, _u8p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "b200zk_fr_batch_invert_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "b200zk_fr_running_product_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, _u8p, C.c_uint32, C.c_void_p]),
+    "b200zk_fr_kate_div_dev": (C.c_int32, [C.c_void_p, C.c_uint64, _u8p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200zk_gate_program_create": (C.c_int32, [C.c_void_p, C.c_uint32, _u8p, C.c_uint32, C.c_void_p, C.c_uint32, _u8p, C.c_uint32,
+                                               C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "b200zk_gate_program_set_const": (C.c_int32, [C.c_uint64, C.c_uint32, _u8p]),
+    "b200zk_gate_program_run_dev": (C.c_int32, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "b200zk_gate_program_release": (C.c_int32, [C.c_uint64]),
     "b200zk_g1_synth_bases_dev": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "b200zk_selftest_field": (C.c_int32, [C.c_uint32, C.c_uint32, _u8p, _u8p, _u8p, C.c_uint64]),
     "b200zk_microbench": (C.c_int32, [C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

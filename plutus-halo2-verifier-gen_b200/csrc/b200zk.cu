@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "b200zk.h"
+#include "ctx.hpp"
 #include "field.cuh"
 #include "g1.cuh"
 #include "msm.cuh"
@@ -712,6 +713,19 @@ int32_t get_generator_dev(uint32_t** out, cudaStream_t s) {
 
 }  // namespace
 
+// what b200zk_ext.cu shares with this context (ctx.hpp)
+namespace b200zk_ctx {
+int32_t fail(int32_t code, const std::string& msg) { return ::fail(code, msg); }
+std::mutex& mutex() { return g_mu; }
+int32_t need_init() { return ::need_init(); }
+cudaStream_t stream() { return g.stream; }
+int sm_count() { return g.prop.multiProcessorCount; }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int32_t generator_dev(uint32_t** out, cudaStream_t s) { return get_generator_dev(out, s); }
+static std::vector<void (*)()> g_hooks;
+void on_shutdown(void (*fn)()) { g_hooks.push_back(fn); }
+}  // namespace b200zk_ctx
+
 // ==========================================================================================
 // C ABI
 // ==========================================================================================
@@ -747,6 +761,7 @@ int32_t b200zk_shutdown(void) {
     if (!g.inited) return B200ZK_OK;
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
+    for (auto fn : b200zk_ctx::g_hooks) fn();
     for (auto& kv : g.tables) cudaFree(kv.second.d);
     g.tables.clear();
     for (auto& kv : g.ntt_plans) {

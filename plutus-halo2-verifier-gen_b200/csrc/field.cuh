@@ -101,8 +101,8 @@ HD void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
 // __constant__ copies (they fold into IMAD operands as c[bank][off]); the host copies exist
 // only for the CPU-side algorithm tests.
 #if defined(__CUDACC__)
-__device__ __constant__ uint32_t c_fp_p[12] = B200ZK_FP_P, c_fp_pm2[12] = B200ZK_FP_PM2, c_fp_r[12] = B200ZK_FP_R, c_fp_r2[12] = B200ZK_FP_R2;
-__device__ __constant__ uint32_t c_fr_p[8] = B200ZK_FR_P, c_fr_pm2[8] = B200ZK_FR_PM2, c_fr_r[8] = B200ZK_FR_R, c_fr_r2[8] = B200ZK_FR_R2;
+static __device__ __constant__ uint32_t c_fp_p[12] = B200ZK_FP_P, c_fp_pm2[12] = B200ZK_FP_PM2, c_fp_r[12] = B200ZK_FP_R, c_fp_r2[12] = B200ZK_FP_R2;
+static __device__ __constant__ uint32_t c_fr_p[8] = B200ZK_FR_P, c_fr_pm2[8] = B200ZK_FR_PM2, c_fr_r[8] = B200ZK_FR_R, c_fr_r2[8] = B200ZK_FR_R2;
 #endif
 static const uint32_t h_fp_p[12] = B200ZK_FP_P, h_fp_pm2[12] = B200ZK_FP_PM2, h_fp_r[12] = B200ZK_FP_R, h_fp_r2[12] = B200ZK_FP_R2;
 static const uint32_t h_fr_p[8] = B200ZK_FR_P, h_fr_pm2[8] = B200ZK_FR_PM2, h_fr_r[8] = B200ZK_FR_R, h_fr_r2[8] = B200ZK_FR_R2;

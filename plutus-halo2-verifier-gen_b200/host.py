@@ -238,3 +238,191 @@ def g1_compress(affine: bytes) -> bytes:
     out = C.create_string_buffer(48)
     check(lib().b200zk_g1_compress(addr(affine), addr(out)))
     return out.raw
+
+
+def g1_decompress_batch(compressed: bytes, strict: bool = True) -> Tuple[bytes, List[int]]:
+    """Decompresses n 48-byte points on the GPU (the proof's commitments, transcript.ak:62-83).
+    Returns (n * 96 bytes of affine wire format, per-point status).  With ``strict`` a bad encoding
+    raises like the in-tree uncompress does (CompressUncompress.hs:70-100); otherwise the caller reads
+    the status list (0 ok, 1 not compressed, 2 bad infinity, 3 x >= p, 4 not on the curve)."""
+    if len(compressed) % 48:
+        raise ValueError("compressed points are 48 bytes each")
+    n = len(compressed) // 48
+    out = C.create_string_buffer(96 * max(n, 1))
+    status = (C.c_uint32 * max(n, 1))()
+    rc = lib().b200zk_g1_decompress_batch(addr(compressed), n, addr(out), C.addressof(status))
+    if rc != 0 and (strict or rc != -7):
+        check(rc)
+    return out.raw[:96 * n], [status[i] for i in range(n)]
+
+
+# ------------------------------------------------------------------------------------------------
+# Device-resident columns and the polynomial side of the prover (SURVEY.md 8f): everything below keeps
+# its data in HBM between calls; only scalars and results the transcript needs cross the bus.
+# ------------------------------------------------------------------------------------------------
+class DeviceBuffer:
+    """A raw HBM allocation made through the C ABI (no CUDA runtime on the caller's side)."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p(0)
+        check(lib().b200zk_dev_alloc(C.byref(p), nbytes))
+        self.ptr = p.value
+        self.nbytes = nbytes
+
+    def upload(self, data: bytes, offset: int = 0) -> None:
+        assert offset + len(data) <= self.nbytes
+        check(lib().b200zk_dev_upload(self.ptr + offset, addr(data), len(data)))
+
+    def download(self, nbytes: Optional[int] = None, offset: int = 0) -> bytes:
+        nbytes = self.nbytes - offset if nbytes is None else nbytes
+        out = C.create_string_buffer(max(nbytes, 1))
+        check(lib().b200zk_dev_download(addr(out), self.ptr + offset, nbytes))
+        return out.raw[:nbytes]
+
+    def free(self) -> None:
+        if self.ptr:
+            check(lib().b200zk_dev_free(self.ptr))
+            self.ptr = None
+
+
+class FrVec(DeviceBuffer):
+    """n Fr elements in HBM, Montgomery form (the in-memory form of midnight_curves::Fq)."""
+
+    def __init__(self, n: int):
+        super().__init__(32 * max(n, 1))
+        self.n = n
+
+    @classmethod
+    def from_canonical(cls, data: bytes) -> "FrVec":
+        v = cls(len(data) // 32)
+        if v.n:
+            v.upload(data)
+            check(lib().b200zk_fr_convert_dev(v.ptr, v.ptr, v.n, 1, None))
+        return v
+
+    @classmethod
+    def from_ints(cls, xs: Sequence[int]) -> "FrVec":
+        return cls.from_canonical(b"".join(fr_bytes(x) for x in xs))
+
+    def to_canonical(self) -> bytes:
+        if not self.n:
+            return b""
+        tmp = FrVec(self.n)
+        check(lib().b200zk_fr_convert_dev(self.ptr, tmp.ptr, self.n, 0, None))
+        out = tmp.download(32 * self.n)
+        tmp.free()
+        return out
+
+    def to_ints(self) -> List[int]:
+        b = self.to_canonical()
+        return [int.from_bytes(b[32 * i:32 * i + 32], "little") for i in range(self.n)]
+
+
+POINTWISE_MUL, POINTWISE_ADD, POINTWISE_SUB, POINTWISE_SCALE, POINTWISE_MULADD = 0, 1, 2, 3, 4
+
+
+def fr_pointwise(op: int, a: FrVec, b: Optional[FrVec] = None, scalar: Optional[int] = None, out: Optional[FrVec] = None) -> FrVec:
+    out = out or FrVec(a.n)
+    sb = fr_bytes(scalar) if scalar is not None else None
+    check(lib().b200zk_fr_pointwise_dev(op, a.ptr, b.ptr if b else None, addr(sb), out.ptr, a.n, None))
+    return out
+
+
+def fr_lincomb(polys: Sequence[FrVec], coeffs: Sequence[int], out: Optional[FrVec] = None) -> FrVec:
+    """sum_k coeffs[k] * polys[k]: the x1 / x2 / x4 combinations of multi_open (pcs/kzg.rs:55-79)."""
+    n = polys[0].n
+    out = out or FrVec(n)
+    ptrs = (C.c_void_p * len(polys))(*[p.ptr for p in polys])
+    cb = b"".join(fr_bytes(c) for c in coeffs)
+    check(lib().b200zk_fr_lincomb_dev(C.addressof(ptrs), addr(cb), len(polys), out.ptr, n, None))
+    return out
+
+
+def fr_batch_invert(v: FrVec, out: Optional[FrVec] = None) -> FrVec:
+    out = out or FrVec(v.n)
+    check(lib().b200zk_fr_batch_invert_dev(v.ptr, out.ptr, v.n, None))
+    return out
+
+
+def fr_running_product(v: FrVec, init: Optional[int] = None, inclusive: bool = False, out: Optional[FrVec] = None) -> FrVec:
+    """z_0 = init, z_{i+1} = z_i v_i (permutation / lookup grand products)."""
+    out = out or FrVec(v.n)
+    ib = fr_bytes(init) if init is not None else None
+    check(lib().b200zk_fr_running_product_dev(v.ptr, out.ptr, v.n, addr(ib), 1 if inclusive else 0, None))
+    return out
+
+
+def fr_kate_div(p: FrVec, z: int, want_quotient: bool = True) -> Tuple[Optional[FrVec], int]:
+    """(q, p(z)) with p(X) - p(z) = q(X) (X - z), one sweep over the coefficients."""
+    quot = FrVec(max(p.n - 1, 0)) if want_quotient else None
+    ev = FrVec(1)
+    zb = fr_bytes(z)
+    check(lib().b200zk_fr_kate_div_dev(p.ptr, p.n, addr(zb), quot.ptr if quot else None, ev.ptr, None))
+    e = ev.to_ints()[0]
+    ev.free()
+    return quot, e
+
+
+class GateProgram:
+    """A gate program resident on the device: the numerator of the quotient polynomial as a register
+    machine over the extended-domain columns (include/b200zk.h, b200zk_gate_program_*)."""
+
+    def __init__(self, words: Sequence[int], consts: Sequence[int], rotations: Sequence[int], n_columns: int, k: int,
+                 extended_k: int, t_inv: Optional[Sequence[int]] = None):
+        self.extended_k = extended_k
+        self.n_columns = n_columns
+        w = (C.c_uint32 * max(len(words), 1))(*words)
+        cb = b"".join(fr_bytes(c) for c in consts)
+        rot = (C.c_int32 * max(len(rotations), 1))(*rotations)
+        tb, log_period = None, 0
+        if t_inv is not None:
+            tb = b"".join(fr_bytes(t) for t in t_inv)
+            log_period = len(t_inv).bit_length() - 1
+            assert 1 << log_period == len(t_inv)
+        h = C.c_uint64(0)
+        check(lib().b200zk_gate_program_create(C.addressof(w), len(words) // 4, addr(cb), len(consts), C.addressof(rot),
+                                               len(rotations), addr(tb), log_period, n_columns, k, extended_k, C.byref(h)))
+        self.handle = h.value
+
+    def set_const(self, index: int, value: int) -> None:
+        vb = fr_bytes(value)
+        check(lib().b200zk_gate_program_set_const(self.handle, index, addr(vb)))
+
+    def run(self, columns: Sequence[FrVec], out: Optional[FrVec] = None, accumulate: bool = False) -> FrVec:
+        assert len(columns) == self.n_columns
+        out = out or FrVec(1 << self.extended_k)
+        ptrs = (C.c_void_p * max(len(columns), 1))(*[c.ptr for c in columns])
+        check(lib().b200zk_gate_program_run_dev(self.handle, C.addressof(ptrs), out.ptr, 1 if accumulate else 0, None))
+        return out
+
+    def release(self) -> None:
+        if self.handle:
+            check(lib().b200zk_gate_program_release(self.handle))
+            self.handle = None
+
+
+def srs_generate(s: int, k: int, want_lagrange: bool = True) -> Tuple[DeviceBuffer, Optional[DeviceBuffer]]:
+    """ParamsKZG::unsafe_setup's two G1 tables for secret s, left in HBM as packed Montgomery affine
+    points (src/kzg_params.rs:33-80 caches what this produces)."""
+    n = 1 << k
+    g = DeviceBuffer(96 * n)
+    gl = DeviceBuffer(96 * n) if want_lagrange else None
+    sb = fr_bytes(s)
+    wb = fr_bytes(pow(ROOT_OF_UNITY, 1 << (TWO_ADICITY - k), R_MOD))
+    check(lib().b200zk_srs_generate_dev(addr(sb), k, addr(wb), g.ptr, gl.ptr if gl else None, None))
+    return g, gl
+
+
+def g1_export(buf: DeviceBuffer, n: int) -> bytes:
+    out = C.create_string_buffer(96 * max(n, 1))
+    check(lib().b200zk_g1_export_dev(buf.ptr, n, addr(out)))
+    return out.raw[:96 * n]
+
+
+def params_unsafe_setup(k: int, s: int) -> ParamsKZG:
+    """SRS generated and registered without leaving the device."""
+    g, gl = srs_generate(s, k)
+    params = ParamsKZG.from_device(k, g.ptr, gl.ptr)
+    g.free()
+    gl.free()
+    return params

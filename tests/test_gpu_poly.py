@@ -1,0 +1,188 @@
+"""Parity of the polynomial-side Fr kernels with the big-int oracle, through the
+C ABI: pointwise ops, linear combinations, batched inversion, running products, evaluation + Kate division,
+and gate programs over the extended domain; plus size-independent identities at 2^20..2^22."""
+import random
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+def rand_fr(rng, n, zeros=0.0):
+    return [0 if rng.random() < zeros else rng.randrange(R) for _ in range(n)]
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 255, 2047, 2048, 2049, 4096 + 17, 70001])
+def test_running_product_and_batch_invert(gpu, pyref, n):
+    rng = random.Random(n)
+    H = gpu.host
+    v = rand_fr(rng, n, zeros=0.02 if n > 40 else 0.0)
+    dv = H.FrVec.from_ints(v)
+    assert H.fr_batch_invert(dv).to_ints() == pyref.batch_invert(v)
+    nz = [x or 1 for x in v]
+    dn = H.FrVec.from_ints(nz)
+    assert H.fr_running_product(dn).to_ints() == pyref.running_product(nz)
+    init = rng.randrange(R)
+    assert H.fr_running_product(dn, init=init, inclusive=True).to_ints() == pyref.running_product(nz, init, True)
+    # in place
+    H.fr_running_product(dn, out=dn)
+    assert dn.to_ints() == pyref.running_product(nz)
+    H.fr_batch_invert(dv, out=dv)
+    assert dv.to_ints() == pyref.batch_invert(v)
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 2047, 2048, 2049, 3 * 2048 + 5, 50000])
+def test_kate_division_and_evaluation(gpu, pyref, n):
+    rng = random.Random(1000 + n)
+    H = gpu.host
+    c = rand_fr(rng, n)
+    for z in (rng.randrange(R), 0, 1, R - 1):
+        dq, ev = H.fr_kate_div(H.FrVec.from_ints(c), z)
+        q, e = pyref.kate_div(c, z)
+        assert ev == e == pyref.poly_eval(c, z)
+        assert dq.to_ints() == q
+        _, ev2 = H.fr_kate_div(H.FrVec.from_ints(c), z, want_quotient=False)
+        assert ev2 == e
+
+
+def test_pointwise_and_lincomb(gpu, pyref):
+    rng = random.Random(7)
+    H = gpu.host
+    n = 5000
+    a, b = rand_fr(rng, n), rand_fr(rng, n)
+    da, db = H.FrVec.from_ints(a), H.FrVec.from_ints(b)
+    assert H.fr_pointwise(H.POINTWISE_MUL, da, db).to_ints() == [x * y % R for x, y in zip(a, b)]
+    assert H.fr_pointwise(H.POINTWISE_ADD, da, db).to_ints() == [(x + y) % R for x, y in zip(a, b)]
+    assert H.fr_pointwise(H.POINTWISE_SUB, da, db).to_ints() == [(x - y) % R for x, y in zip(a, b)]
+    s = rng.randrange(R)
+    assert H.fr_pointwise(H.POINTWISE_SCALE, da, scalar=s).to_ints() == [x * s % R for x in a]
+    acc = H.FrVec.from_ints(a)
+    H.fr_pointwise(H.POINTWISE_MULADD, da, db, out=acc)
+    assert acc.to_ints() == [(x * y + x) % R for x, y in zip(a, b)]
+    for count in (1, 3, 16, 17, 40):
+        polys = [rand_fr(rng, 700) for _ in range(count)]
+        coeffs = rand_fr(rng, count)
+        got = H.fr_lincomb([H.FrVec.from_ints(p) for p in polys], coeffs).to_ints()
+        assert got == pyref.lincomb(polys, coeffs), count
+    # canonical <-> Montgomery round trip keeps the bytes
+    raw = b"".join(x.to_bytes(32, "little") for x in a)
+    assert H.FrVec.from_canonical(raw).to_canonical() == raw
+
+
+def random_program(rng, pyref, n_cols, n_rot, n_consts, n_instr, max_regs=48):
+    prog, written = [], []
+    for _ in range(n_instr):
+        def src():
+            kinds = ["col", "const"] + (["reg"] * 2 if written else [])
+            k = rng.choice(kinds)
+            if k == "col":
+                return pyref.gate_col(rng.randrange(n_cols), rng.randrange(n_rot))
+            if k == "const":
+                return pyref.gate_const(rng.randrange(n_consts))
+            return pyref.gate_reg(rng.choice(written))
+        op = rng.randrange(8)
+        dst = rng.randrange(max_regs)
+        prog.append((op, dst, src(), src(), src()))
+        if dst not in written:
+            written.append(dst)
+    return prog
+
+
+@pytest.mark.parametrize("k,ext_k,seed", [(3, 5, 1), (4, 4, 2), (5, 7, 3), (6, 8, 4)])
+def test_gate_program_vs_oracle(gpu, pyref, k, ext_k, seed):
+    rng = random.Random(seed)
+    H = gpu.host
+    n_ext = 1 << ext_k
+    n_cols, rotations = 5, [0, 1, -1, 2, -3]
+    consts = rand_fr(rng, 6)
+    cols = [rand_fr(rng, n_ext) for _ in range(n_cols)]
+    prog = random_program(rng, pyref, n_cols, len(rotations), len(consts), 60)
+    t_inv = pyref.vanishing_inverse_on_coset(7, k, ext_k) if ext_k > k else None
+    gp = H.GateProgram(pyref.gate_program_words(prog), consts, rotations, n_cols, k, ext_k, t_inv)
+    dcols = [H.FrVec.from_ints(c) for c in cols]
+    out = gp.run(dcols)
+    want = pyref.gate_eval(prog, consts, rotations, cols, k, ext_k, t_inv)
+    assert out.to_ints() == want
+    # accumulate mode and a changed challenge
+    gp.set_const(2, 12345)
+    consts2 = list(consts)
+    consts2[2] = 12345
+    gp.run(dcols, out=out, accumulate=True)
+    want2 = pyref.gate_eval(prog, consts2, rotations, cols, k, ext_k, t_inv)
+    assert out.to_ints() == [(a + b) % R for a, b in zip(want, want2)]
+    gp.release()
+
+
+def test_gate_program_plonk_gate_vanishes(gpu, pyref):
+    """The standard arithmetic gate q_m a b + q_l a + q_r b + q_o c + q_c over a satisfying trace: the numerator
+    vanishes on H, so the quotient times (X^n - 1) reproduces it on the coset, and the quotient has degree < 2n."""
+    rng = random.Random(99)
+    H = gpu.host
+    k, ext_k = 6, 8
+    n, n_ext = 1 << k, 1 << ext_k
+    a, b = rand_fr(rng, n), rand_fr(rng, n)
+    qm, ql, qr, qo = rand_fr(rng, n), rand_fr(rng, n), rand_fr(rng, n), [R - 1] * n
+    c = [(qm[i] * a[i] * b[i] + ql[i] * a[i] + qr[i] * b[i]) % R for i in range(n)]
+    qc = [0] * n
+    dom = H.EvaluationDomain(4, k, g_coset=7)
+    assert dom.extended_k == ext_k
+
+    def extend(vals):  # Lagrange values -> extended coset evaluations, staying on the device after the upload
+        coeff = dom.lagrange_to_coeff(b"".join(x.to_bytes(32, "little") for x in vals))
+        return H.FrVec.from_canonical(dom.coeff_to_extended(coeff))
+
+    cols = [extend(v) for v in (a, b, c, qm, ql, qr, qo, qc)]
+    P = pyref
+    prog = [
+        (P.GATE_OPS["mul"], 0, P.gate_col(0, 0), P.gate_col(1, 0), 0),
+        (P.GATE_OPS["mul"], 0, P.gate_reg(0), P.gate_col(3, 0), 0),
+        (P.GATE_OPS["muladd"], 0, P.gate_col(4, 0), P.gate_col(0, 0), P.gate_reg(0)),
+        (P.GATE_OPS["muladd"], 0, P.gate_col(5, 0), P.gate_col(1, 0), P.gate_reg(0)),
+        (P.GATE_OPS["muladd"], 0, P.gate_col(6, 0), P.gate_col(2, 0), P.gate_reg(0)),
+        (P.GATE_OPS["add"], 0, P.gate_reg(0), P.gate_col(7, 0), 0),
+    ]
+    t_inv = P.vanishing_inverse_on_coset(7, k, ext_k)
+    gp = H.GateProgram(P.gate_program_words(prog), [], [0], 8, k, ext_k, t_inv)
+    h_ext = gp.run(cols)
+    h_coeff = dom.extended_to_coeff(h_ext.to_canonical())           # n * 3 low coefficients
+    full = H.EvaluationDomain._ntt                                   # all 2^ext_k coefficients: the top n must be zero
+    buf = bytearray(h_ext.to_canonical())
+    full(buf, ext_k, dom.extended_omega_inv, gpu.NTT_INVERSE_SCALE | gpu.NTT_COSET_OUT, dom.g_coset_inv)
+    assert bytes(buf[:len(h_coeff)]) == h_coeff
+    assert bytes(buf[32 * 2 * n:]) == bytes(32 * (n_ext - 2 * n)), "quotient degree must stay below 2n for a degree-3 gate"
+    assert any(buf[:32 * n])
+    gp.release()
+
+
+def test_gate_program_rejects_bad_programs(gpu, pyref):
+    H = gpu.host
+    P = pyref
+    with pytest.raises(gpu.B200zkError):   # reads a register that was never written
+        H.GateProgram(P.gate_program_words([(0, 0, P.gate_reg(3), P.gate_const(0), 0)]), [1], [0], 1, 3, 4)
+    with pytest.raises(gpu.B200zkError):   # column out of range
+        H.GateProgram(P.gate_program_words([(7, 0, P.gate_col(2, 0), 0, 0)]), [1], [0], 1, 3, 4)
+    with pytest.raises(gpu.B200zkError):   # destination register out of range
+        H.GateProgram(P.gate_program_words([(7, 48, P.gate_const(0), 0, 0)]), [1], [0], 1, 3, 4)
+
+
+@pytest.mark.parametrize("log_n", [20, 22])
+def test_large_identities(gpu, oracle, pyref, log_n):
+    """Size-independent properties at sizes the big-int oracle cannot walk: (i) the quotient and the evaluation of
+    one sweep satisfy p(z') = q(z') (z' - z) + p(z) at a second point; (ii) the running product of v times the
+    running product of 1/v is all ones."""
+    H = gpu.host
+    n = 1 << log_n
+    rng = random.Random(log_n)
+    p = H.FrVec.from_canonical(oracle.synth_scalars(77, 0, n))
+    z, z2 = rng.randrange(R), rng.randrange(R)
+    q, pz = H.fr_kate_div(p, z)
+    _, pz2 = H.fr_kate_div(p, z2, want_quotient=False)
+    _, qz2 = H.fr_kate_div(q, z2, want_quotient=False)
+    assert pz2 == (qz2 * (z2 - z) + pz) % R
+    inv = H.fr_batch_invert(p)
+    prod = H.fr_running_product(p, inclusive=True)
+    iprod = H.fr_running_product(inv, inclusive=True)
+    ones = H.fr_pointwise(H.POINTWISE_MUL, prod, iprod).to_canonical()
+    assert ones == (1).to_bytes(32, "little") * n

@@ -1,0 +1,69 @@
+"""CPU checks of the polynomial-side / SRS oracle functions (oracle/pyref.py) against independent formulations,
+so that the GPU parity tests compare against a checker that has itself been cross-checked."""
+import random
+
+R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+def test_kate_div_reconstructs(pyref):
+    rng = random.Random(1)
+    for n in (1, 2, 9, 64):
+        c = [rng.randrange(R) for _ in range(n)]
+        z = rng.randrange(R)
+        q, e = pyref.kate_div(c, z)
+        assert e == pyref.poly_eval(c, z) == sum(ci * pow(z, i, R) for i, ci in enumerate(c)) % R
+        rec = [0] * n
+        for i, qi in enumerate(q):
+            rec[i + 1] = (rec[i + 1] + qi) % R
+            rec[i] = (rec[i] - qi * z) % R
+        rec[0] = (rec[0] + e) % R
+        assert rec == c
+
+
+def test_running_product_and_inverse(pyref):
+    rng = random.Random(2)
+    v = [rng.randrange(1, R) for _ in range(50)] + [0]
+    inv = pyref.batch_invert(v)
+    assert inv[-1] == 0 and all(a * b % R == 1 for a, b in zip(v[:-1], inv[:-1]))
+    ex = pyref.running_product(v[:-1], 5)
+    assert ex[0] == 5 and ex[3] == 5 * v[0] * v[1] * v[2] % R
+    assert pyref.running_product(v[:-1], 5, True)[:-1] == ex[1:]
+
+
+def test_srs_scalars_are_the_lagrange_basis(pyref):
+    s, k = 0xDEADBEEF, 4
+    mono, lag = pyref.srs_scalars(s, k)
+    n, w = 1 << k, pyref.omega(k)
+    assert sum(lag) % R == 1
+    rng = random.Random(3)
+    f = [rng.randrange(R) for _ in range(n)]
+    evals = pyref.ntt(f, w)
+    assert sum(l * e for l, e in zip(lag, evals)) % R == sum(m * c for m, c in zip(mono, f)) % R == pyref.poly_eval(f, s)
+    # same formula the verifier uses for its Lagrange evaluations (lagrange.ak:80-100)
+    rot = [pow(w, i, R) for i in range(n)]
+    assert lag == pyref.lagrange_basis(s, pow(s, n, R), pyref.fr_inv(n), rot)
+
+
+def test_vanishing_inverse_periodicity(pyref):
+    k, ext_k, g = 3, 5, 7
+    t = pyref.vanishing_inverse_on_coset(g, k, ext_k)
+    w = pyref.omega(ext_k)
+    for j in range(1 << ext_k):
+        x = g * pow(w, j, R) % R
+        assert t[j % len(t)] * (pow(x, 1 << k, R) - 1) % R == 1
+
+
+def test_gate_eval_matches_direct_formula(pyref):
+    rng = random.Random(4)
+    k = ext_k = 3
+    n = 1 << k
+    a, b = [rng.randrange(R) for _ in range(n)], [rng.randrange(R) for _ in range(n)]
+    P = pyref
+    prog = [(P.GATE_OPS["mul"], 1, P.gate_col(0, 0), P.gate_col(1, 1), 0),
+            (P.GATE_OPS["muladd"], 2, P.gate_reg(1), P.gate_const(0), P.gate_col(0, 2)),
+            (P.GATE_OPS["sub"], 0, P.gate_reg(2), P.gate_reg(1), 0)]
+    got = P.gate_eval(prog, [5], [0, 1, -1], [a, b], k, ext_k)
+    for i in range(n):
+        m = a[i] * b[(i + 1) % n] % R
+        assert got[i] == (m * 5 + a[(i - 1) % n] - m) % R
+    assert P.gate_program_words(prog)[:4] == [2 | (1 << 8), 2 << 28, (2 << 28) | (1 << 12) | 1, 0]
