@@ -124,7 +124,7 @@ struct Ctx {
     MsmPlan last_plan{};
     // MSM workspace
     DevBuf scalars, counts, offsets, cursor, ntask, task_off, entries, task_bucket, task_start, task_len, buckets,
-        partials, len_hist, len_off, order, heavy, heavy_items, aff_a, aff_b, aff_pre, redS[2], redA[2], scan_tmp[2], out_mont, out_canon, stage, flag;
+        partials, len_hist, len_off, order, heavy, heavy_items, adhoc, aff_a, aff_b, aff_pre, redS[2], redA[2], scan_tmp[2], out_mont, out_canon, stage, flag;
     // NTT workspace
     DevBuf ntt_data, ntt_tmp[2], small;
 };
@@ -776,7 +776,7 @@ int32_t b200zk_shutdown(void) {
     g.coset_tables.clear();
     if (g.fixed_table) { cudaFree(g.fixed_table); g.fixed_table = nullptr; }
     DevBuf* all[] = {&g.scalars, &g.counts, &g.offsets, &g.cursor, &g.ntask, &g.task_off, &g.entries, &g.task_bucket,
-                     &g.task_start, &g.task_len, &g.buckets, &g.partials, &g.len_hist, &g.len_off, &g.order, &g.heavy, &g.heavy_items, &g.aff_a, &g.aff_b, &g.aff_pre, &g.redS[0], &g.redS[1], &g.redA[0], &g.redA[1],
+                     &g.task_start, &g.task_len, &g.buckets, &g.partials, &g.len_hist, &g.len_off, &g.order, &g.heavy, &g.heavy_items, &g.adhoc, &g.aff_a, &g.aff_b, &g.aff_pre, &g.redS[0], &g.redS[1], &g.redA[0], &g.redA[1],
                      &g.scan_tmp[0], &g.scan_tmp[1], &g.out_mont, &g.out_canon, &g.stage, &g.flag, &g.ntt_data,
                      &g.ntt_tmp[0], &g.ntt_tmp[1], &g.small};
     for (DevBuf* b : all) b->release();
@@ -820,10 +820,10 @@ static int32_t register_common(const uint8_t* d_src, uint64_t n, uint32_t fmt_fl
     uint32_t fmt = fmt_flags & 0xffu;
     // Window tables: W rows of n points.  Built for resident SRS tables (they are registered once and
     // committed against many times); skipped on request, for tiny tables, or when HBM is short.
-    bool want_rows = !(fmt_flags & B200ZK_BASES_NO_WINDOW_TABLES) && !g.tune_no_tables && n >= 1024;
+    bool want_rows = !(fmt_flags & B200ZK_BASES_NO_WINDOW_TABLES) && !g.tune_no_tables && n >= 1;
     uint32_t c = 0, W = 1;
     if (want_rows) {
-        c = (g.tune_c >= 2 && g.tune_c <= 24) ? g.tune_c : msm_choose_window(n, 1, true);
+        c = (g.tune_c >= 2 && g.tune_c <= 24) ? g.tune_c : std::max(msm_choose_window(n, 1, true), 8u);   // c >= 8: at most 32 rows
         W = (256 + c - 1) / c;
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
@@ -925,14 +925,35 @@ int32_t b200zk_msm_g1(uint64_t bases, uint64_t offset, const uint8_t* scalars, u
 
 int32_t b200zk_msm_g1_adhoc(const uint8_t* g1_affine, uint32_t point_fmt, const uint8_t* scalars, uint32_t scalar_fmt,
                             uint64_t n, uint8_t out_affine[96]) {
-    uint64_t h = 0;
-    int32_t rc = b200zk_bases_register(g1_affine, n, point_fmt | B200ZK_BASES_NO_WINDOW_TABLES, 96, &h);
-    if (rc != B200ZK_OK) return rc;
-    rc = b200zk_msm_g1(h, 0, scalars, n, scalar_fmt, out_affine);
-    std::string keep = t_err;
-    b200zk_bases_release(h);
-    if (rc != B200ZK_OK) t_err = keep;
-    return rc;
+    // One pass on the context stream with cached workspaces: no table registration, no allocation, one
+    // synchronisation at the end (the verifier calls this once per proof or per batch).
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(need_init());
+    if (!out_affine || ((!g1_affine || !scalars) && n)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    if (point_fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown point format");
+    if (scalar_fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown scalar format");
+    if (n == 0) { memset(out_affine, 0, 96); return B200ZK_OK; }
+    cudaStream_t s = g.stream;
+    TRY(g.stage.ensure(n * 96 + 16));
+    TRY(g.adhoc.ensure(n * 96));
+    TRY(g.scalars.ensure(n * 32 + 16));
+    TRY(g.out_canon.ensure(96));
+    TRY(g.flag.ensure(4));
+    CU(cudaMemcpyAsync(g.stage.p, g1_affine, n * 96, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(g.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(g.flag.p, 0, 4, s));
+    LAUNCH(g1_ingest_kernel, (unsigned)((n + 127) / 128), 128, 0, s, (const uint8_t*)g.stage.as<uint8_t>(), n, 96u,
+           point_fmt == B200ZK_FMT_MONT ? 1u : 0u, g.adhoc.as<uint32_t>(), g.flag.as<uint32_t>());
+    BaseTable t;
+    t.d = g.adhoc.as<uint32_t>();
+    t.n = n;
+    TRY(msm_run(&t, t.d, g.scalars.as<uint32_t>(), n, 1, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), s));
+    uint32_t bad = 0;
+    CU(cudaMemcpyAsync(out_affine, g.out_canon.p, 96, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&bad, g.flag.p, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (bad) { memset(out_affine, 0, 96); return fail(B200ZK_ERR_BAD_POINT, "a base point is not a canonical point on the curve"); }
+    return B200ZK_OK;
 }
 
 int32_t b200zk_msm_g1_dev(uint64_t bases, uint64_t offset, const void* d_scalars, uint64_t n, uint32_t batch,

@@ -460,20 +460,113 @@ __global__ void __launch_bounds__(128) msm_reduce_coop_kernel(const uint32_t* __
 }
 
 // ---------------------------------------------------------------------------------------
+// Warp-cooperative point operations for the serial chains of the tail (window combine, partial sums).
+// A chain of c*(W-1) dependent doublings is inherent to a 255-bit MSM over bases without window tables
+// (the verifier's ad-hoc sums, small tables); what can be cut is the latency of ONE doubling.  A single
+// thread pays ~9 dependent-latency-bound field products per doubling (measured 10 us); here all 32 lanes
+// hold the same point and the independent products of each level of the formula run on different lanes,
+// then are broadcast: 3 product levels per doubling, 4 per full addition.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ Fp fp_bcast(const Fp& v, int src) {
+    Fp r;
+#pragma unroll
+    for (int k = 0; k < 12; k++) r.l[k] = __shfl_sync(0xffffffffu, v.l[k], src);
+    return r;
+}
+__device__ __forceinline__ void fp_pick(Fp& dst, const Fp& v, bool take) {
+#pragma unroll
+    for (int k = 0; k < 12; k++) dst.l[k] = take ? v.l[k] : dst.l[k];
+}
+// all lanes must call these with identical (replicated) arguments
+__device__ __noinline__ void warp_xyzz_dbl(G1Xyzz& a) {
+    if (xyzz_is_inf(a)) return;
+    const uint32_t lane = threadIdx.x & 31;
+    Fp u = fe_dbl(a.y);
+    // level 1: V = U^2 (lane 0), X^2 (lane 1)
+    Fp o = u;
+    fp_pick(o, a.x, lane == 1);
+    Fp t = fp_mul_call(o, o);
+    Fp v = fp_bcast(t, 0), xx = fp_bcast(t, 1);
+    Fp m = fe_add(fe_dbl(xx), xx);
+    // level 2: W = U*V (0), S = X*V (1), M^2 (2), ZZ3 = V*ZZ (3)
+    Fp p = u, q = v;
+    fp_pick(p, a.x, lane == 1);
+    fp_pick(p, m, lane == 2);
+    fp_pick(q, m, lane == 2);
+    fp_pick(p, a.zz, lane == 3);
+    t = fp_mul_call(p, q);
+    Fp w = fp_bcast(t, 0), sx = fp_bcast(t, 1), mm = fp_bcast(t, 2), zz3 = fp_bcast(t, 3);
+    Fp x3 = fe_sub(fe_sub(mm, sx), sx);
+    // level 3: M*(S - X3) (0), W*Y (1), ZZZ3 = W*ZZZ (2)
+    p = m; q = fe_sub(sx, x3);
+    fp_pick(p, w, lane >= 1);
+    fp_pick(q, a.y, lane == 1);
+    fp_pick(q, a.zzz, lane == 2);
+    t = fp_mul_call(p, q);
+    Fp y3 = fe_sub(fp_bcast(t, 0), fp_bcast(t, 1));
+    a.zzz = fp_bcast(t, 2);
+    a.zz = zz3;
+    a.x = x3;
+    a.y = y3;
+}
+__device__ __noinline__ void warp_xyzz_add(G1Xyzz& a, const G1Xyzz& b) {
+    if (xyzz_is_inf(b)) return;
+    if (xyzz_is_inf(a)) { a = b; return; }
+    const uint32_t lane = threadIdx.x & 31;
+    // level 1: U1 = X1*ZZ2 (0), U2 = X2*ZZ1 (1), S1 = Y1*ZZZ2 (2), S2 = Y2*ZZZ1 (3), ZZ1*ZZ2 (4), ZZZ1*ZZZ2 (5)
+    Fp p = a.x, q = b.zz;
+    fp_pick(p, b.x, lane == 1);   fp_pick(q, a.zz, lane == 1);
+    fp_pick(p, a.y, lane == 2);   fp_pick(q, b.zzz, lane == 2);
+    fp_pick(p, b.y, lane == 3);   fp_pick(q, a.zzz, lane == 3);
+    fp_pick(p, a.zz, lane == 4);
+    fp_pick(p, a.zzz, lane == 5); fp_pick(q, b.zzz, lane == 5);
+    Fp t = fp_mul_call(p, q);
+    Fp u1 = fp_bcast(t, 0), u2 = fp_bcast(t, 1), s1 = fp_bcast(t, 2), s2 = fp_bcast(t, 3), zz12 = fp_bcast(t, 4), zzz12 = fp_bcast(t, 5);
+    Fp pp_ = fe_sub(u2, u1), r = fe_sub(s2, s1);
+    if (fe_is_zero(pp_)) {
+        if (fe_is_zero(r)) warp_xyzz_dbl(a);
+        else xyzz_set_inf(a);
+        return;
+    }
+    // level 2: P^2 (0), R^2 (1)
+    p = pp_;
+    fp_pick(p, r, lane == 1);
+    t = fp_mul_call(p, p);
+    Fp pp = fp_bcast(t, 0), rr = fp_bcast(t, 1);
+    // level 3: PPP = P*PP (0), Q = U1*PP (1), ZZ3 = ZZ12*PP (2)
+    p = pp_;
+    fp_pick(p, u1, lane == 1);
+    fp_pick(p, zz12, lane == 2);
+    t = fp_mul_call(p, pp);
+    Fp ppp = fp_bcast(t, 0), qq = fp_bcast(t, 1), zz3 = fp_bcast(t, 2);
+    Fp x3 = fe_sub(fe_sub(fe_sub(rr, ppp), qq), qq);
+    // level 4: R*(Q - X3) (0), S1*PPP (1), ZZZ3 = ZZZ12*PPP (2)
+    p = r; q = fe_sub(qq, x3);
+    fp_pick(p, s1, lane == 1);
+    fp_pick(p, zzz12, lane == 2);
+    fp_pick(q, ppp, lane >= 1);
+    t = fp_mul_call(p, q);
+    a.y = fe_sub(fp_bcast(t, 0), fp_bcast(t, 1));
+    a.zzz = fp_bcast(t, 2);
+    a.zz = zz3;
+    a.x = x3;
+}
+
+// ---------------------------------------------------------------------------------------
 // 8. window combine + affine normalisation.  out_mont: 24 limbs Montgomery affine;
 //    out_canon: 24 limbs canonical (the wire format), either may be null.
 // ---------------------------------------------------------------------------------------
-__global__ void msm_combine_kernel(const uint32_t* __restrict__ win_sums, uint32_t W, uint32_t c,
-                                   uint32_t* out_mont, uint32_t* out_canon, uint32_t* out_xyzz) {
-    if (threadIdx.x != 0) return;
-    const uint32_t b = blockIdx.x;             // one block per batch item
+__global__ void __launch_bounds__(32) msm_combine_kernel(const uint32_t* __restrict__ win_sums, uint32_t W, uint32_t c,
+                                                         uint32_t* out_mont, uint32_t* out_canon, uint32_t* out_xyzz) {
+    const uint32_t b = blockIdx.x;             // one warp per batch item, every lane holds the same accumulator
     G1Xyzz acc;
     xyzz_set_inf(acc);
     for (int w = (int)W - 1; w >= 0; w--) {
-        for (uint32_t k = 0; k < c; k++) xyzz_dbl_ni(acc);
+        for (uint32_t k = 0; k < c && w != (int)W - 1; k++) warp_xyzz_dbl(acc);
         G1Xyzz s = xyzz_ld(win_sums, (uint64_t)b * W + w);
-        xyzz_add_ni(acc, s);
+        warp_xyzz_add(acc, s);
     }
+    if (threadIdx.x != 0) return;
     if (out_xyzz) xyzz_st(out_xyzz, b, acc);               // un-normalised partial (multi-GPU exchange)
     if (!out_mont && !out_canon) return;
     G1Affine a = xyzz_to_affine_ni(acc);
@@ -482,14 +575,15 @@ __global__ void msm_combine_kernel(const uint32_t* __restrict__ win_sums, uint32
 }
 
 // sum of n XYZZ partial points -> affine: the combine step of the point-range sharded MSM
-__global__ void g1_sum_xyzz_kernel(const uint32_t* __restrict__ pts, uint32_t n, uint32_t* out_mont, uint32_t* out_canon) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    G1Xyzz acc;
+__global__ void __launch_bounds__(32) g1_sum_xyzz_kernel(const uint32_t* __restrict__ pts, uint32_t n, uint32_t* out_mont, uint32_t* out_canon) {
+    if (blockIdx.x != 0) return;
+    G1Xyzz acc;                                            // one warp, replicated accumulator
     xyzz_set_inf(acc);
     for (uint32_t i = 0; i < n; i++) {
         G1Xyzz p = xyzz_ld(pts, i);
-        xyzz_add_ni(acc, p);
+        warp_xyzz_add(acc, p);
     }
+    if (threadIdx.x != 0) return;
     G1Affine a = xyzz_to_affine_ni(acc);
     if (out_mont) { fp_st(out_mont, a.x); fp_st(out_mont + 12, a.y); }
     if (out_canon) { fp_st(out_canon, fe_from_mont(a.x)); fp_st(out_canon + 12, fe_from_mont(a.y)); }
