@@ -180,6 +180,9 @@ int32_t b200zk_g1_export_dev(const void *d_points_mont, uint64_t n, uint8_t *out
 
 /* ---- Fr vectors: the polynomial side of multi_open and of the permutation / lookup arguments ------- */
 int32_t b200zk_fr_convert_dev(const void *d_in, void *d_out, uint64_t n, uint32_t to_mont, void *stream);
+/* `batch` polynomials of n_in coefficients -> n_out coefficients each, zero padded: the staging step of
+ * EvaluationDomain::coeff_to_extended when the coefficients already live in HBM (d_out must not overlap d_in) */
+int32_t b200zk_fr_extend_dev(const void *d_in, uint64_t n_in, void *d_out, uint64_t n_out, uint32_t batch, void *stream);
 /* op 0: out = a*b, 1: a+b, 2: a-b, 3: a*scalar, 4: out += a*b   (in place allowed) */
 int32_t b200zk_fr_pointwise_dev(uint32_t op, const void *d_a, const void *d_b, const uint8_t scalar[32], void *d_out,
                                 uint64_t n, void *stream);
@@ -226,7 +229,8 @@ int32_t b200zk_selftest_field(uint32_t field, uint32_t op, const uint8_t *a, con
 /* integer-pipe micro-benchmark: kind 0 = independent IMAD.WIDE.U32, 1 = IMAD lo+hi pairs, 2 = Fp Montgomery
  * multiplications, 3 = XYZZ mixed additions, 4 = Fr multiplications, 5 = carry-chained IMAD.WIDE.U32.X rows
  * (as the Montgomery multiplier issues them), 6 = DFMA, 7 = IMAD.WIDE with carry-out only, 8 = IMAD.WIDE
- * paired 1:1 with IADD.  *out_ops_per_s receives limb-MACs (0,1,5,7,8), multiplications (2,4), additions (3)
+ * paired 1:1 with IADD, 9 = IMAD.HI.U32 alone, 10 = 32-bit IMAD alone, 11 = the unfused IMAD + IMAD.HI.U32 pair with an
+ * immediate multiplier.  *out_ops_per_s receives limb-MACs (0,1,5,7,8), multiplications (2,4), additions (3)
  * or FMAs (6) per second over all SMs.                                                            */
 int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double *out_ops_per_s, double *out_ms);
 /* number of kernels this library has launched since init (bench.py's gpu_launches counter) */

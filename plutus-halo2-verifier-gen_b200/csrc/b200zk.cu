@@ -115,7 +115,7 @@ struct Ctx {
     std::map<NttKey, NttPlan> ntt_plans;
     std::map<CosetKey, uint32_t*> coset_tables;
     uint32_t* fixed_table = nullptr;  // 8 x 256 multiples of G for the synthetic-base generator
-    uint32_t tune_c = 0, tune_smax = 0, tune_variant = 3, tune_no_tables = 0;
+    uint32_t tune_c = 0, tune_smax = 0, tune_variant = 6, tune_no_tables = 0;
     // phase timing (b200zk_set_profiling): events recorded on the launching stream
     bool profiling = false;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -301,6 +301,7 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
         switch (g.tune_variant) {
             case 1: LAUNCH(msm_accumulate_kernel_v1, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
             case 2: LAUNCH(msm_accumulate_kernel_v2, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
+            case 6: LAUNCH(msm_accumulate_kernel_v6, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
             case 3: LAUNCH(msm_accumulate_kernel_v3, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
             case 4:
             case 5: {
@@ -657,6 +658,35 @@ __global__ void __launch_bounds__(256) mb_imad_alu_kernel(uint64_t* out, uint32_
     uint64_t s = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) s ^= acc[k] + x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// MODE 0: IMAD.HI.U32 only; 1: 32-bit IMAD only; 2: unfused pair IMAD + IMAD.HI.U32 on the same operands with an
+// immediate multiplier (what ptxas emits for the m*p rows when the modulus limb is not in a plain register).
+// The multiplicand rotates through the accumulators so that nothing can be hoisted.
+template <int MODE>
+__global__ void __launch_bounds__(256) mb_imad_parts_kernel(uint64_t* out, uint32_t iters, uint32_t a0, uint32_t b0) {
+    uint32_t lo[8], hi[8];
+    uint32_t b = b0 + blockIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { lo[k] = a0 + threadIdx.x * 8 + k; hi[k] = k + 1; }
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (MODE == 0) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(hi[k]) : "r"(hi[(k + 1) & 7]), "r"(b));
+                else if (MODE == 1) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[k]) : "r"(lo[(k + 1) & 7]), "r"(b));
+                else {
+                    uint32_t m = lo[(k + 1) & 7];
+                    asm volatile("mad.lo.cc.u32 %0, %2, 0x53bda402, %0;\n\tmadc.hi.u32 %1, %2, 0x53bda402, %1;"
+                                 : "+r"(lo[k]), "+r"(hi[k]) : "r"(m));
+                }
+            }
+        }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= ((uint64_t)hi[k] << 32) | lo[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 template <class P>
@@ -1101,7 +1131,7 @@ int32_t b200zk_selftest_field(uint32_t field, uint32_t op, const uint8_t* a, con
 int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double* out_ops_per_s, double* out_ms) {
     std::lock_guard<std::mutex> lk(g_mu);
     TRY(need_init());
-    if (kind > 8 || !out_ops_per_s) return fail(B200ZK_ERR_INVALID_ARG, "bad microbench arguments");
+    if (kind > 11 || !out_ops_per_s) return fail(B200ZK_ERR_INVALID_ARG, "bad microbench arguments");
     int sms = g.prop.multiProcessorCount;
     unsigned threads = (kind == 3) ? 128 : 256;
     unsigned blocks = (unsigned)sms * ((kind == 3) ? 3 : ((kind == 2) ? 4 : 8));
@@ -1146,6 +1176,18 @@ int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double* out_ops_per_s, 
             case 7:
                 LAUNCH(mb_imad_cout_kernel, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
                 per_thread = 24.0 * iters;
+                break;
+            case 9:
+                LAUNCH(mb_imad_parts_kernel<0>, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
+                per_thread = 32.0 * iters;
+                break;
+            case 10:
+                LAUNCH(mb_imad_parts_kernel<1>, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
+                per_thread = 32.0 * iters;
+                break;
+            case 11:
+                LAUNCH(mb_imad_parts_kernel<2>, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
+                per_thread = 32.0 * iters;
                 break;
             default:
                 LAUNCH(mb_imad_alu_kernel, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
@@ -1196,7 +1238,7 @@ int32_t b200zk_get_profile(uint32_t* kind, double* phase_ms, uint32_t cap, uint3
 int32_t b200zk_set_msm_tuning(uint32_t window_bits, uint32_t smax) {
     std::lock_guard<std::mutex> lk(g_mu);
     g.tune_c = window_bits & 0xffu;
-    g.tune_variant = ((window_bits >> 8) & 0x7fu) ? ((window_bits >> 8) & 0x7fu) - 1 : 3;  // bits 8..14: 1 + accumulate-kernel variant
+    g.tune_variant = ((window_bits >> 8) & 0x7fu) ? ((window_bits >> 8) & 0x7fu) - 1 : 6;  // bits 8..14: 1 + accumulate-kernel variant
     g.tune_no_tables = (window_bits >> 15) & 1u;    // bit 15: do not build window tables at registration
     g.tune_smax = smax;
     return B200ZK_OK;

@@ -284,6 +284,19 @@ int32_t b200zk_fr_convert_dev(const void* d_in, void* d_out, uint64_t n, uint32_
     return B200ZK_OK;
 }
 
+int32_t b200zk_fr_extend_dev(const void* d_in, uint64_t n_in, void* d_out, uint64_t n_out, uint32_t batch, void* stream) {
+    std::lock_guard<std::mutex> lk(ctx::mutex());
+    XTRY(enter());
+    if (batch == 0 || n_out == 0) return B200ZK_OK;
+    if (!d_in || !d_out) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    if (n_in > n_out) return ctx::fail(B200ZK_ERR_INVALID_ARG, "extend: n_in exceeds n_out");
+    if (misaligned(d_in, d_out)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
+    // every polynomial: n_in coefficients followed by zeros up to n_out (the zero padding of coeff_to_extended)
+    XCU(cudaMemsetAsync(d_out, 0, (size_t)batch * n_out * 32, S(stream)));
+    if (n_in) XCU(cudaMemcpy2DAsync(d_out, n_out * 32, d_in, n_in * 32, n_in * 32, batch, cudaMemcpyDeviceToDevice, S(stream)));
+    return B200ZK_OK;
+}
+
 int32_t b200zk_fr_pointwise_dev(uint32_t op, const void* d_a, const void* d_b, const uint8_t scalar[32], void* d_out, uint64_t n,
                                 void* stream) {
     std::lock_guard<std::mutex> lk(ctx::mutex());

@@ -26,6 +26,7 @@ struct G1Xyzz {
 // msm.cuh, an out-of-line call that keeps the code small
 struct MulInline {
     static HD Fp mul(const Fp& a, const Fp& b) { return fe_mul(a, b); }
+    static HD Fp sqr(const Fp& a) { return fe_mul(a, a); }
 };
 
 HD bool g1a_is_inf(const G1Affine& a) { return fe_is_zero(a.x) && fe_is_zero(a.y); }

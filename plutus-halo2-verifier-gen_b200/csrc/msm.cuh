@@ -211,7 +211,8 @@ __device__ __forceinline__ void msm_accumulate_body(const uint32_t* __restrict__
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 64));
         }
         G1Affine pt = g1a_ldg(bases, cur & 0x7fffffffu);
-        if (VARIANT == 3) xyzz_add_mixed_t<MulCall>(acc, pt, (cur >> 31) != 0);
+        if (VARIANT == 6) xyzz_add_mixed_t<MulCallSqr>(acc, pt, (cur >> 31) != 0);
+        else if (VARIANT == 3) xyzz_add_mixed_t<MulCall>(acc, pt, (cur >> 31) != 0);
         else xyzz_add_mixed_t<MulInline>(acc, pt, (cur >> 31) != 0);
     }
     if (lenf & 0x80000000u) xyzz_st(partials, t, acc);
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(MSM_ACC_ARGS) { msm
 __global__ void __launch_bounds__(128, 3) msm_accumulate_kernel_v1(MSM_ACC_ARGS) { msm_accumulate_body<1>(MSM_ACC_PASS); }
 __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel_v2(MSM_ACC_ARGS) { msm_accumulate_body<2>(MSM_ACC_PASS); }
 __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel_v3(MSM_ACC_ARGS) { msm_accumulate_body<3>(MSM_ACC_PASS); }
+__global__ void __launch_bounds__(128, 4) msm_accumulate_kernel_v6(MSM_ACC_ARGS) { msm_accumulate_body<6>(MSM_ACC_PASS); }
 
 // Variants 4/5: batched affine additions (affine_tree.cuh), one thread per task as above.
 __device__ __noinline__ Fp fp_inv_fast_call(Fp a) { return fe_inv_fast(a); }

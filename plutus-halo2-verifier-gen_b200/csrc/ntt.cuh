@@ -139,8 +139,23 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     const uint64_t cmask = ((uint64_t)1 << a.log_cols) - 1;
 
     // ---- load: element (ul, j) <- x[poly*n + u + j*(n/R)], ul fastest so consecutive lanes read
-    //      consecutive u
+    //      consecutive u.  The plain path (no scaling) is unrolled so that the eight loads are in flight together;
+    //      the scaled paths keep one copy of the product (code size: the kernel must stay in the instruction cache)
+    if (!a.in_scale && !a.reduce_in) {
 #pragma unroll
+        for (int t = 0; t < 8; t++) {
+            uint32_t idx = tid + t * NTT_THREADS;
+            uint32_t ul = idx & ((1u << logU) - 1), j = idx >> logU;
+            uint64_t col = col0 + ul;
+            Fr v = fe_zero<FrParams>();
+            if (col < a.total_cols) {
+                uint64_t poly = col >> a.log_cols, u = col & cmask;
+                v = ntt_ld(a.in + 8 * ((poly << a.log_n) + u + ((uint64_t)j << a.log_cols)));
+            }
+            ntt_sts(sm, (ul << deg) | j, v);
+        }
+    } else
+#pragma unroll 1
     for (int t = 0; t < 8; t++) {
         uint32_t idx = tid + t * NTT_THREADS;
         uint32_t ul = idx & ((1u << logU) - 1), j = idx >> logU;
@@ -172,7 +187,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     // ---- store: y[poly*n + q + s*(R*p + k)] = X_u[k] * T[p*R + k]; X_u[k] sits at bitrev(k).
     //      First pass (s = 1): k fastest.  Later passes: ul (-> q) fastest.
     const bool k_fast = (a.log_s == 0);
-#pragma unroll
+#pragma unroll 1
     for (int t = 0; t < 8; t++) {
         uint32_t idx = tid + t * NTT_THREADS;
         uint32_t ul, k;

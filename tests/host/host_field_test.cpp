@@ -46,6 +46,8 @@ template <class P> static int check_field(const char* name,
         Fe<P> r = fe_from_mont(fe_mul(am, bm)), e;
         omul((uint8_t*)a.l, (uint8_t*)b.l, (uint8_t*)e.l);
         if (!fe_eq(r, e)) { bad++; if (bad < 5) printf("%s mul mismatch it=%d\n", name, it); }
+        r = fe_from_mont(fe_sqr_fast(am)); omul((uint8_t*)a.l, (uint8_t*)a.l, (uint8_t*)e.l);
+        if (!fe_eq(r, e) || !fe_eq(fe_sqr_fast(am), fe_mul(am, am))) { bad++; if (bad < 5) printf("%s sqr_fast mismatch it=%d\n", name, it); }
         r = fe_from_mont(fe_add(am, bm)); oadd((uint8_t*)a.l, (uint8_t*)b.l, (uint8_t*)e.l);
         if (!fe_eq(r, e)) { bad++; if (bad < 5) printf("%s add mismatch it=%d\n", name, it); }
         r = fe_from_mont(fe_sub(am, bm)); osub((uint8_t*)a.l, (uint8_t*)b.l, (uint8_t*)e.l);

@@ -13,7 +13,8 @@ zk = importlib.import_module("plutus-halo2-verifier-gen_b200")
 def run(iters=2000):
     zk.init(-1)
     names = {0: "imad_wide_lmac_per_s", 1: "imad_lohi_lmac_per_s", 2: "fp_mul_per_s", 3: "xyzz_madd_per_s", 4: "fr_mul_per_s",
-             5: "imad_wide_carry_chain_lmac_per_s", 6: "dfma_per_s", 7: "imad_wide_carry_out_lmac_per_s", 8: "imad_wide_plus_iadd_lmac_per_s"}
+             5: "imad_wide_carry_chain_lmac_per_s", 6: "dfma_per_s", 7: "imad_wide_carry_out_lmac_per_s", 8: "imad_wide_plus_iadd_lmac_per_s",
+             9: "imad_hi_only_per_s", 10: "imad_lo_only_per_s", 11: "imad_unfused_pair_imm_lmac_per_s"}
     out = {"device": zk.device_info()}
     for kind, name in names.items():
         ops, ms = C.c_double(), C.c_double()
