@@ -23,6 +23,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402  (scalar generator, oracle loader)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 #            name: (k, proof commitments, of which uniform (h pieces + f + pi + random poly))
 CIRCUITS = {
@@ -114,6 +115,50 @@ def main():
         msm_ms = (time.perf_counter() - t0) / args.reps * 1e3
         rec = {"circuit": name, "k": k, "commitments": ncom, "ntt_columns": ncols, "gpu_trace_ms": gpu_ms, "gpu_msm_ms": msm_ms,
                "gpu_ntt_ms": gpu_ms - msm_ms, "gpu_launches": launches, "timed": "host clock, host buffers in and out"}
+        # ---- the same proof with columns resident in HBM: witness columns go up once (Lagrange values),
+        # everything between them and the commitments stays on the device: commit_lagrange, lagrange_to_coeff,
+        # zero-padded coeff_to_extended, a gate program for the quotient numerator with 1/(X^n - 1) fused,
+        # extended_to_coeff, commitment of the quotient pieces; only the G1 points come back.
+        import random as _random
+        from poly_bench import atms_like_program
+        n_ext = 1 << ek
+        rng = _random.Random(k)
+        words, _muls, n_instr = atms_like_program(ncols, 4, max(4, ncols), rng)
+        t_inv = [rng.randrange(1, zk.host.R_MOD) for _ in range(4)]
+        gp = zk.host.GateProgram(words, [rng.randrange(zk.host.R_MOD), 0], [0, 1, -1, 2], ncols, k, ek, t_inv)
+        d_cols = torch.empty(32 * n * ncom, dtype=torch.uint8, device="cuda")
+        d_ext = torch.empty(32 * n_ext * ncols, dtype=torch.uint8, device="cuda")
+        d_h = torch.empty(32 * n_ext, dtype=torch.uint8, device="cuda")
+        d_pts = torch.empty(96 * (ncom + 3), dtype=torch.uint8, device="cuda")
+        h_pts = torch.zeros(96 * (ncom + 3), dtype=torch.uint8).pin_memory()
+        col_ptrs = (C.c_void_p * ncols)(*[d_ext.data_ptr() + 32 * n_ext * i for i in range(ncols)])
+        MONT = zk.NTT_MONT
+
+        def resident_trace():
+            d_cols.copy_(sc, non_blocking=True)                                            # H2D once: ncom * n * 32 bytes
+            zk.capi.check(lib.b200zk_fr_convert_dev(d_cols.data_ptr(), d_cols.data_ptr(), n * ncom, 1, st))
+            zk.capi.check(lib.b200zk_msm_g1_dev(h.value, 0, d_cols.data_ptr(), n, ncom, zk.FMT_MONT, 0, d_pts.data_ptr(), st))
+            zk.capi.check(lib.b200zk_ntt_fr_dev(d_cols.data_ptr(), ncols, k, zk.capi.addr(omega_inv), zk.NTT_INVERSE_SCALE | MONT, 0, st))
+            zk.capi.check(lib.b200zk_fr_extend_dev(d_cols.data_ptr(), n, d_ext.data_ptr(), n_ext, ncols, st))
+            zk.capi.check(lib.b200zk_ntt_fr_dev(d_ext.data_ptr(), ncols, ek, zk.capi.addr(omega_ext_b), zk.NTT_COSET_IN | MONT, zk.capi.addr(g), st))
+            zk.capi.check(lib.b200zk_gate_program_run_dev(gp.handle, C.addressof(col_ptrs), d_h.data_ptr(), 0, st))
+            zk.capi.check(lib.b200zk_ntt_fr_dev(d_h.data_ptr(), 1, ek, zk.capi.addr(omega_ext_inv),
+                                                zk.NTT_INVERSE_SCALE | zk.NTT_COSET_OUT | MONT, zk.capi.addr(gi), st))
+            zk.capi.check(lib.b200zk_msm_g1_dev(h.value, 0, d_h.data_ptr(), n, 3, zk.FMT_MONT, 0, d_pts.data_ptr() + 96 * ncom, st))
+            h_pts.copy_(d_pts, non_blocking=True)
+            torch.cuda.synchronize()
+
+        resident_trace()
+        assert bytes(h_pts[:96 * ncom].numpy()) == bytes(out.numpy()), "resident commitments differ from the host-buffer path"
+        t0 = time.perf_counter()
+        for _ in range(args.reps):
+            resident_trace()
+        rec["gpu_resident_trace_ms"] = (time.perf_counter() - t0) / args.reps * 1e3
+        rec["resident_note"] = ("columns uploaded once and kept in HBM: %d commitments + %d inverse NTTs + %d coset NTTs of 2^%d + gate program "
+                                "(%d instructions over %d columns) + quotient inverse NTT + 3 quotient commitments; D2H = %d bytes"
+                                % (ncom, ncols, ncols, ek, n_instr, ncols, 96 * (ncom + 3)))
+        gp.release()
+        del d_cols, d_ext, d_h
         if L is not None:
             bases = np.empty(96 * n, dtype=np.uint8)
             L.orc_g1_synth_bases(0xB200, 0, n, bases.ctypes.data, 0)
