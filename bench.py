@@ -358,7 +358,7 @@ def main():
                     "d2h_bytes_per_step": 96, "ms_per_step": e2e_s * 1e3,
                     "timed": "host clock around synchronous public calls (H2D scalars, MSM, exchange, D2H result)"},
             "gpu_launches": gpu_launches,
-            "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved / 1e12,
+            "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel_v6", "achieved": achieved / 1e12,
                          "peak": imad_peak / 1e12, "unit": "Tlimb-MAC/s", "frac": achieved / imad_peak if imad_peak else None,
                          "traffic": ncu_traffic("r01_ncu_msm_accumulate_2p24.json", 1) if (args.log_n == 24 and world == 1) else None,
                          "traffic_note": "bytes per launch of the accumulate kernel (ncu capture of this command, profiles/); "
@@ -368,6 +368,12 @@ def main():
                                  "(CUDA events on the launching stream, last timed step, max over ranks); peak = IMAD.WIDE.U32 "
                                  "micro-benchmark measured in this run; window bits actually used: %s"
                                  % (LMAC_PER_POINT, n_local, prof.get("window_bits")),
+                         "issued_imad_wide_frac": (2756.0 * n_local * (prof.get("windows") or 0) / (acc_ms * 1e-3)) / imad_peak
+                         if (acc_ms and imad_peak) else None,
+                         "issued_note": "IMAD.WIDE actually issued by the kernel (8 products x 289 + 2 squarings x 222 per mixed "
+                                        "addition, one addition per point and table row) / time / peak: the pipe utilisation; "
+                                        "`frac` above uses the fixed 16-window accounting of SURVEY 8d and exceeds it when window "
+                                        "tables allow fewer rows",
                          "phases_ms": {k: prof.get(k) for k in ("sort", "accumulate", "tail")},
                          "hbm_crosscheck_gbs": n_local * 128 / (acc_ms * 1e-3) / 1e9 if acc_ms else None,
                          "hbm_peak_gbs": peaks.get("hbm_gbs")},

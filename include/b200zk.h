@@ -180,6 +180,9 @@ int32_t b200zk_g1_export_dev(const void *d_points_mont, uint64_t n, uint8_t *out
 
 /* ---- Fr vectors: the polynomial side of multi_open and of the permutation / lookup arguments ------- */
 int32_t b200zk_fr_convert_dev(const void *d_in, void *d_out, uint64_t n, uint32_t to_mont, void *stream);
+/* out[r * cols + c] = base^((row0 + r) * c), Montgomery form: the twiddle block omega^(i2 * k1) between the two
+ * halves of a four-step transform (the multi-GPU NTT of dist.py multiplies by it with b200zk_fr_pointwise_dev) */
+int32_t b200zk_fr_power_table_dev(const uint8_t base[32], uint64_t row0, uint64_t rows, uint64_t cols, void *d_out, void *stream);
 /* `batch` polynomials of n_in coefficients -> n_out coefficients each, zero padded: the staging step of
  * EvaluationDomain::coeff_to_extended when the coefficients already live in HBM (d_out must not overlap d_in) */
 int32_t b200zk_fr_extend_dev(const void *d_in, uint64_t n_in, void *d_out, uint64_t n_out, uint32_t batch, void *stream);

@@ -71,6 +71,7 @@ SIGNATURES = {
     "b200zk_g1_fixed_mul_dev": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]),
     "b200zk_g1_export_dev": (C.c_int32, [C.c_void_p, C.c_uint64, _u8p]),
     "b200zk_fr_convert_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "b200zk_fr_power_table_dev": (C.c_int32, [_u8p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "b200zk_fr_extend_dev": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
     "b200zk_fr_pointwise_dev": (C.c_int32, [C.c_uint32, C.c_void_p, C.c_void_p, _u8p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "b200zk_fr_lincomb_dev": (C.c_int32, [C.c_void_p, _u8p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]),

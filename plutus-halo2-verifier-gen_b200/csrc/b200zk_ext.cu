@@ -284,6 +284,20 @@ int32_t b200zk_fr_convert_dev(const void* d_in, void* d_out, uint64_t n, uint32_
     return B200ZK_OK;
 }
 
+int32_t b200zk_fr_power_table_dev(const uint8_t base[32], uint64_t row0, uint64_t rows, uint64_t cols, void* d_out, void* stream) {
+    std::lock_guard<std::mutex> lk(ctx::mutex());
+    XTRY(enter());
+    if (rows == 0 || cols == 0) return B200ZK_OK;
+    if (!base || !d_out) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    if (misaligned(d_out)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
+    if (row0 + rows > (1ull << 32) || cols > (1ull << 32)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "power table: exponents exceed 64 bits");
+    uint32_t* d_b = nullptr;
+    XTRY(upload_fr(base, 1, S(stream), &d_b));
+    XLAUNCH(fr_power_table_kernel, blocks(rows * cols, 256), 256, 0, S(stream), (const uint32_t*)d_b, row0, rows, cols,
+            reinterpret_cast<uint32_t*>(d_out));
+    return B200ZK_OK;
+}
+
 int32_t b200zk_fr_extend_dev(const void* d_in, uint64_t n_in, void* d_out, uint64_t n_out, uint32_t batch, void* stream) {
     std::lock_guard<std::mutex> lk(ctx::mutex());
     XTRY(enter());

@@ -108,6 +108,22 @@ __global__ void __launch_bounds__(256) fr_geometric_kernel(const uint32_t* __res
     }
 }
 
+// out[r * cols + c] = base^((row0 + r) * c): the twiddle block omega^(i2 * k1) of a four-step / multi-GPU
+// transform, one thread per entry (square-and-multiply over the 64-bit exponent)
+__global__ void __launch_bounds__(256) fr_power_table_kernel(const uint32_t* __restrict__ base_p, uint64_t row0, uint64_t rows,
+                                                             uint64_t cols, uint32_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    uint64_t r = i / cols, c = i - r * cols;
+    uint64_t e = (row0 + r) * c;
+    Fr b = fr_ldg(base_p), acc = fe_one<FrParams>();
+    for (; e; e >>= 1) {
+        if (e & 1) acc = fr_mul_ni(acc, b);
+        b = fr_mul_ni(b, b);
+    }
+    fr_st(out + 8 * i, acc);
+}
+
 // single-thread helpers: *v <- (*v)^e ;  out <- (s^(2^k) - 1) / 2^k  (the constant of the SRS Lagrange scalars)
 __global__ void fr_pow_small_kernel(uint32_t* v, uint32_t e) {
     Fr b = fr_ld(v), acc = fe_one<FrParams>();
