@@ -129,4 +129,117 @@ private:
     std::vector<G1Affine> lp_, rp_;
 };
 
+
+// ---------------------------------------------------------------------------------------------------
+// Columns resident in HBM (INTEGRATION.md route C): RAII device vectors of Fr in Montgomery
+// form and the polynomial-side operations between the NTTs and the commitments.
+// ---------------------------------------------------------------------------------------------------
+class DeviceFr {
+public:
+    explicit DeviceFr(uint64_t n) : n_(n) { check(b200zk_dev_alloc(&p_, (n ? n : 1) * 32)); }
+    // canonical host values -> Montgomery form on the device
+    explicit DeviceFr(const std::vector<Fr>& v) : DeviceFr(v.size()) {
+        if (n_) {
+            check(b200zk_dev_upload(p_, v.data(), n_ * 32));
+            check(b200zk_fr_convert_dev(p_, p_, n_, 1, nullptr));
+        }
+    }
+    ~DeviceFr() { if (p_) b200zk_dev_free(p_); }
+    DeviceFr(const DeviceFr&) = delete;
+    DeviceFr& operator=(const DeviceFr&) = delete;
+    DeviceFr(DeviceFr&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    void* ptr() const { return p_; }
+    uint64_t size() const { return n_; }
+    std::vector<Fr> to_host() const {   // canonical
+        std::vector<Fr> out(n_);
+        if (!n_) return out;
+        DeviceFr tmp(n_);
+        check(b200zk_fr_convert_dev(p_, tmp.p_, n_, 0, nullptr));
+        check(b200zk_dev_download(out.data(), tmp.p_, n_ * 32));
+        return out;
+    }
+
+private:
+    void* p_ = nullptr;
+    uint64_t n_ = 0;
+};
+
+namespace poly {
+// (q, p(z)) with p(X) - p(z) = q(X) (X - z): the witness polynomials of the KZG multi-open
+// (/root/reference/src/plutus_gen/extraction/pcs/kzg.rs:55-79)
+inline std::pair<DeviceFr, Fr> kate_div(const DeviceFr& p, const Fr& z) {
+    DeviceFr q(p.size() ? p.size() - 1 : 0), ev(1);
+    check(b200zk_fr_kate_div_dev(p.ptr(), p.size(), z.data(), q.ptr(), ev.ptr(), nullptr));
+    return {std::move(q), ev.to_host()[0]};
+}
+inline Fr eval(const DeviceFr& p, const Fr& z) {
+    DeviceFr ev(1);
+    check(b200zk_fr_kate_div_dev(p.ptr(), p.size(), z.data(), nullptr, ev.ptr(), nullptr));
+    return ev.to_host()[0];
+}
+// sum_k coeffs[k] * polys[k]
+inline DeviceFr lincomb(const std::vector<const DeviceFr*>& polys, const std::vector<Fr>& coeffs) {
+    if (polys.empty() || polys.size() != coeffs.size()) throw Error(B200ZK_ERR_INVALID_ARG, "lincomb: polys and coeffs must match");
+    DeviceFr out(polys[0]->size());
+    std::vector<const void*> ptrs;
+    for (auto* q : polys) ptrs.push_back(q->ptr());
+    check(b200zk_fr_lincomb_dev(ptrs.data(), reinterpret_cast<const uint8_t*>(coeffs.data()), (uint32_t)polys.size(), out.ptr(),
+                                out.size(), nullptr));
+    return out;
+}
+// z_0 = 1, z_{i+1} = z_i v_i: the grand products of the permutation / lookup arguments
+inline DeviceFr running_product(const DeviceFr& v, bool inclusive = false) {
+    DeviceFr out(v.size());
+    check(b200zk_fr_running_product_dev(v.ptr(), out.ptr(), v.size(), nullptr, inclusive ? 1u : 0u, nullptr));
+    return out;
+}
+inline DeviceFr batch_invert(const DeviceFr& v) {
+    DeviceFr out(v.size());
+    check(b200zk_fr_batch_invert_dev(v.ptr(), out.ptr(), v.size(), nullptr));
+    return out;
+}
+}  // namespace poly
+
+// The numerator of the quotient polynomial as a device-resident register program (b200zk.h, gate programs).
+class GateProgram {
+public:
+    GateProgram(const std::vector<uint32_t>& words, const std::vector<Fr>& consts, const std::vector<int32_t>& rotations,
+                uint32_t n_columns, uint32_t k, uint32_t extended_k, const std::vector<Fr>& t_inv = {})
+        : ek_(extended_k), ncol_(n_columns) {
+        uint32_t log_period = 0;
+        while ((size_t(1) << log_period) < t_inv.size()) log_period++;
+        check(b200zk_gate_program_create(words.data(), (uint32_t)(words.size() / 4), reinterpret_cast<const uint8_t*>(consts.data()),
+                                         (uint32_t)consts.size(), rotations.data(), (uint32_t)rotations.size(),
+                                         t_inv.empty() ? nullptr : reinterpret_cast<const uint8_t*>(t_inv.data()), log_period,
+                                         n_columns, k, extended_k, &h_));
+    }
+    ~GateProgram() { if (h_) b200zk_gate_program_release(h_); }
+    GateProgram(const GateProgram&) = delete;
+    GateProgram& operator=(const GateProgram&) = delete;
+    void set_challenge(uint32_t index, const Fr& v) { check(b200zk_gate_program_set_const(h_, index, v.data())); }
+    // evaluates the program at every row of the extended domain
+    DeviceFr run(const std::vector<const DeviceFr*>& columns) const {
+        if (columns.size() != ncol_) throw Error(B200ZK_ERR_INVALID_ARG, "gate program: wrong number of columns");
+        DeviceFr out(uint64_t(1) << ek_);
+        std::vector<const void*> ptrs;
+        for (auto* c : columns) ptrs.push_back(c->ptr());
+        check(b200zk_gate_program_run_dev(h_, ptrs.data(), out.ptr(), 0, nullptr));
+        return out;
+    }
+
+private:
+    uint64_t h_ = 0;
+    uint32_t ek_, ncol_;
+};
+
+// Decompresses the commitments a proof carries (48 bytes each); throws on a bad encoding like the in-tree
+// uncompress (/root/reference/plinth-verifier/plutus-halo2/src/Plutus/Crypto/Halo2/CompressUncompress.hs:70-100).
+inline std::vector<G1Affine> g1_decompress_batch(const std::vector<std::array<uint8_t, 48>>& compressed) {
+    std::vector<G1Affine> out(compressed.size());
+    if (!compressed.empty())
+        check(b200zk_g1_decompress_batch(reinterpret_cast<const uint8_t*>(compressed.data()), compressed.size(),
+                                         reinterpret_cast<uint8_t*>(out.data()), nullptr));
+    return out;
+}
+
 }  // namespace b200zk

@@ -426,3 +426,122 @@ def params_unsafe_setup(k: int, s: int) -> ParamsKZG:
     g.free()
     gl.free()
     return params
+
+
+# ------------------------------------------------------------------------------------------------
+# Expression trees -> gate programs.  The Rust side does this once per circuit over halo2's
+# ``Expression<F>`` with the same visitor the reference uses to walk gates
+# (/root/reference/src/plutus_gen/extraction/mod.rs:81-102); this is the same compiler for the Python
+# mirror and the tests.  An expression is a nested tuple:
+#   ("const", int) | ("challenge", i) | ("query", column, rotation) |
+#   ("neg", e) | ("sum", a, b) | ("product", a, b) | ("scaled", e, int)
+# ------------------------------------------------------------------------------------------------
+_OP = {"add": 0, "sub": 1, "mul": 2, "neg": 3, "double": 4, "square": 5, "muladd": 6, "mov": 7}
+GATE_MAX_REGS = 48
+
+
+class CompiledGates:
+    def __init__(self, words, consts, rotations, challenge_slots, n_columns):
+        self.words, self.consts, self.rotations = words, consts, rotations
+        self.challenge_slots = challenge_slots      # challenge index -> constant-table index (for set_const)
+        self.n_columns = n_columns
+
+    def instantiate(self, k: int, extended_k: int, t_inv: Optional[Sequence[int]] = None) -> "GateProgram":
+        return GateProgram(self.words, self.consts, self.rotations, self.n_columns, k, extended_k, t_inv)
+
+
+def compile_gates(gates: Sequence[tuple], n_columns: int, y_challenge: Optional[int] = None) -> CompiledGates:
+    """Compiles the gate expressions into one program whose result is their fold sum_j gate_j * y^(len-1-j) (upstream
+    folds the gates of the quotient numerator with the challenge y); with one gate and no y it is the gate itself."""
+    consts: List[int] = []
+    const_idx: dict = {}
+    chal: dict = {}
+    rots: List[int] = []
+    rot_idx: dict = {}
+    words: List[int] = []
+    free = list(range(GATE_MAX_REGS - 1, 0, -1))       # register 0 is the accumulator of the y-fold
+
+    def K(v):
+        key = ("k", v % R_MOD)
+        if key not in const_idx:
+            const_idx[key] = len(consts)
+            consts.append(v % R_MOD)
+        return (0 << 28) | const_idx[key]
+
+    def CH(i):
+        if i not in chal:
+            chal[i] = len(consts)
+            consts.append(0)
+        return (0 << 28) | chal[i]
+
+    def ROT(r):
+        if r not in rot_idx:
+            rot_idx[r] = len(rots)
+            rots.append(r)
+        return rot_idx[r]
+
+    def emit(op, dst, a, b=0, c=0):
+        words.extend([_OP[op] | (dst << 8), a, b, c])
+
+    def alloc():
+        if not free:
+            raise ValueError("expression needs more than %d registers; split it into several programs" % GATE_MAX_REGS)
+        return free.pop()
+
+    def release(src):
+        if src >> 28 == 1 and (src & 0x0FFFFFFF) != 0:
+            free.append(src & 0x0FFFFFFF)
+
+    def go(e):
+        """Returns a source operand holding the value of e (a leaf is used in place, anything else lands in a register)."""
+        kind = e[0]
+        if kind == "const":
+            return K(e[1])
+        if kind == "challenge":
+            return CH(e[1])
+        if kind == "query":
+            if not 0 <= e[1] < n_columns:
+                raise ValueError("query of column %d outside the %d columns" % (e[1], n_columns))
+            return (2 << 28) | (e[1] << 12) | ROT(e[2])
+        if kind == "neg":
+            a = go(e[1])
+            release(a)
+            d = alloc()
+            emit("neg", d, a)
+            return (1 << 28) | d
+        if kind == "scaled":
+            a = go(e[1])
+            release(a)
+            d = alloc()
+            emit("mul", d, a, K(e[2]))
+            return (1 << 28) | d
+        if kind in ("sum", "product"):
+            # a*b + c in one instruction when a sum has a product on one side
+            if kind == "sum" and e[1][0] == "product":
+                x, y_, z = go(e[1][1]), go(e[1][2]), go(e[2])
+                for s_ in (x, y_, z):
+                    release(s_)
+                d = alloc()
+                emit("muladd", d, x, y_, z)
+                return (1 << 28) | d
+            a, b = go(e[1]), go(e[2])
+            release(a)
+            release(b)
+            d = alloc()
+            emit("add" if kind == "sum" else "mul", d, a, b)
+            return (1 << 28) | d
+        raise ValueError("unknown expression node %r" % (kind,))
+
+    if not gates:
+        raise ValueError("no gates")
+    ysrc = CH(y_challenge) if y_challenge is not None else None
+    for j, g in enumerate(gates):
+        v = go(g)
+        if j == 0:
+            emit("mov", 0, v)
+        elif ysrc is None:
+            emit("add", 0, (1 << 28) | 0, v)
+        else:
+            emit("muladd", 0, (1 << 28) | 0, ysrc, v)
+        release(v)
+    return CompiledGates(words, consts, rots, chal, n_columns)

@@ -108,3 +108,22 @@ def test_affine_tree_on_host(oracle):
                            "-L", os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "affine tree: ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_cpp_header_mirror_compiles_and_fails_loudly(zk):
+    """include/b200zk.hpp (the C++ mirror of the reference-facing interface, incl. the resident-column classes) compiles
+    against the library; without a GPU b200zk::init throws the NO_DEVICE error instead of falling back."""
+    src = "/tmp/b200zk_hpp_check.cpp"
+    exe = "/tmp/b200zk_hpp_check"
+    open(src, "w").write(
+        '#include "b200zk.hpp"\n'
+        'int main() {\n'
+        '    using namespace b200zk;\n'
+        '    try { init(); } catch (const Error& e) { return e.code == B200ZK_ERR_NO_DEVICE ? 42 : 1; }\n'
+        '    DeviceFr v(std::vector<Fr>(8)); auto q = poly::kate_div(v, Fr{}); (void)q; return 0;\n'
+        '}\n')
+    libdir = os.path.join(ROOT, "plutus-halo2-verifier-gen_b200")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", libdir, "-lb200zk",
+                           "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    rc = subprocess.run([exe]).returncode
+    assert rc == (0 if _has_gpu() else 42)

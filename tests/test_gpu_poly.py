@@ -186,3 +186,37 @@ def test_large_identities(gpu, oracle, pyref, log_n):
     iprod = H.fr_running_product(inv, inclusive=True)
     ones = H.fr_pointwise(H.POINTWISE_MUL, prod, iprod).to_canonical()
     assert ones == (1).to_bytes(32, "little") * n
+
+
+def test_compiled_gates_on_device(gpu, pyref):
+    """Expression trees -> host.compile_gates -> device program over extended-domain columns (rotations scaled by
+    2^(ext_k - k), challenges set after creation), against direct evaluation of the trees."""
+    from test_oracle_poly import _eval_expr, _sample_gates
+    rng = random.Random(21)
+    H = gpu.host
+    k, ext_k = 5, 7
+    n_ext, scale = 1 << ext_k, 1 << (ext_k - k)
+    cols = [rand_fr(rng, n_ext) for _ in range(6)]
+    challenges = {0: rng.randrange(R), 1: rng.randrange(R), 2: rng.randrange(R)}
+    gates = _sample_gates()
+    cg = H.compile_gates(gates, 6, y_challenge=0)
+    gp = cg.instantiate(k, ext_k)
+    for ci, slot in cg.challenge_slots.items():
+        gp.set_const(slot, challenges[ci])
+    out = gp.run([H.FrVec.from_ints(c) for c in cols]).to_ints()
+
+    def scaled(e):   # the same trees with rotations expressed in extended-domain rows
+        if e[0] == "query":
+            return ("query", e[1], e[2] * scale)
+        if e[0] in ("const", "challenge"):
+            return e
+        if e[0] == "scaled":
+            return ("scaled", scaled(e[1]), e[2])
+        return (e[0],) + tuple(scaled(x) for x in e[1:])
+
+    for row in range(n_ext):
+        want = 0
+        for g in gates:
+            want = (want * challenges[0] + _eval_expr(scaled(g), cols, row, n_ext, challenges)) % R
+        assert out[row] == want, row
+    gp.release()

@@ -67,3 +67,57 @@ def test_gate_eval_matches_direct_formula(pyref):
         m = a[i] * b[(i + 1) % n] % R
         assert got[i] == (m * 5 + a[(i - 1) % n] - m) % R
     assert P.gate_program_words(prog)[:4] == [2 | (1 << 8), 2 << 28, (2 << 28) | (1 << 12) | 1, 0]
+
+
+def _eval_expr(e, cols, row, n, challenges):
+    k = e[0]
+    if k == "const":
+        return e[1] % R
+    if k == "challenge":
+        return challenges[e[1]]
+    if k == "query":
+        return cols[e[1]][(row + e[2]) % n]
+    if k == "neg":
+        return -_eval_expr(e[1], cols, row, n, challenges) % R
+    if k == "scaled":
+        return _eval_expr(e[1], cols, row, n, challenges) * e[2] % R
+    a, b = _eval_expr(e[1], cols, row, n, challenges), _eval_expr(e[2], cols, row, n, challenges)
+    return (a + b) % R if k == "sum" else a * b % R
+
+
+def _sample_gates():
+    q = lambda c, r=0: ("query", c, r)
+    plonk = ("sum", ("sum", ("product", ("product", q(3), q(0)), q(1)), ("product", q(4), q(0))),
+             ("sum", ("product", q(5), q(1)), ("sum", ("neg", q(2)), ("const", 7))))
+    perm = ("product", ("sum", q(0, 1), ("product", ("challenge", 1), q(1, -1))),
+            ("sum", ("scaled", q(2), 5), ("challenge", 2)))
+    boolean = ("product", q(0), ("sum", q(0), ("neg", ("const", 1))))
+    return [plonk, perm, boolean]
+
+
+def test_compile_gates_matches_tree_evaluation(zk, pyref):
+    """host.compile_gates (the Python twin of the Rust-side compiler) against direct evaluation of the expression trees,
+    through the checker's gate-program interpreter: single gates and the y-fold."""
+    rng = random.Random(11)
+    k = 4
+    n = 1 << k
+    cols = [[rng.randrange(R) for _ in range(n)] for _ in range(6)]
+    challenges = {0: rng.randrange(R), 1: rng.randrange(R), 2: rng.randrange(R)}
+    gates = _sample_gates()
+    for subset, y in ((gates[:1], None), (gates, 0), (gates[1:], None)):
+        cg = zk.host.compile_gates(subset, 6, y_challenge=y)
+        consts = list(cg.consts)
+        for ci, slot in cg.challenge_slots.items():
+            consts[slot] = challenges[ci]
+        prog = [(cg.words[4 * i] & 0xFF, cg.words[4 * i] >> 8, cg.words[4 * i + 1], cg.words[4 * i + 2], cg.words[4 * i + 3])
+                for i in range(len(cg.words) // 4)]
+        got = pyref.gate_eval(prog, consts, cg.rotations, cols, k, k)
+        for row in range(n):
+            vals = [_eval_expr(g, cols, row, n, challenges) for g in subset]
+            if y is None:
+                want = sum(vals) % R
+            else:
+                want = 0
+                for v in vals:
+                    want = (want * challenges[y] + v) % R
+            assert got[row] == want, (row, y)
