@@ -127,6 +127,10 @@ struct Ctx {
         partials, len_hist, len_off, order, heavy, heavy_items, adhoc, aff_a, aff_b, aff_pre, redS[2], redA[2], scan_tmp[2], out_mont, out_canon, stage, flag;
     // NTT workspace
     DevBuf ntt_data, ntt_tmp[2], small;
+    // cross-stream ordering of the shared workspaces
+    cudaEvent_t ws_event = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_used = false;
 };
 Ctx g;
 
@@ -135,6 +139,21 @@ int32_t prof_mark(int idx, cudaStream_t s) {
     if (!g.ev[idx]) CU(cudaEventCreate(&g.ev[idx]));
     CU(cudaEventRecord(g.ev[idx], s));
     g.ev_count = idx + 1;
+    return B200ZK_OK;
+}
+
+// The MSM / NTT workspaces are shared by every call of the process.  Calls on one stream are ordered by the
+// stream itself; when a call arrives on a different stream than the previous one, that stream is made to wait
+// for the previous call's last kernel, so callers may use any stream without racing on the workspaces.
+int32_t ws_enter(cudaStream_t s) {
+    if (!g.ws_event) CU(cudaEventCreateWithFlags(&g.ws_event, cudaEventDisableTiming));
+    if (g.ws_used && s != g.ws_stream) CU(cudaStreamWaitEvent(s, g.ws_event, 0));
+    return B200ZK_OK;
+}
+int32_t ws_leave(cudaStream_t s) {
+    CU(cudaEventRecord(g.ws_event, s));
+    g.ws_stream = s;
+    g.ws_used = true;
     return B200ZK_OK;
 }
 
@@ -258,6 +277,7 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     uint32_t* buckets = g.buckets.as<uint32_t>();
     uint32_t* partials = g.partials.as<uint32_t>();
 
+    TRY(ws_enter(s));
     g.ev_kind = 1;
     TRY(prof_mark(0, s));
     CU(cudaMemsetAsync(counts, 0, (NBt + 1) * 4, s));
@@ -353,6 +373,7 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     } while (m > 1);
     LAUNCH(msm_combine_kernel, batch, 32, 0, s, win_sums, pl.precomp ? 1u : pl.W, pl.c, d_out_mont, d_out_canon, d_out_xyzz);
     TRY(prof_mark(3, s));
+    TRY(ws_leave(s));
     g.last_plan = pl;
     return B200ZK_OK;
 }
@@ -486,6 +507,7 @@ int32_t ntt_run(uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t 
     }
     uint32_t log_s = 0;
     const uint32_t* src = d_data;
+    TRY(ws_enter(s));
     g.ev_kind = 2;
     TRY(prof_mark(0, s));
     for (uint32_t i = 0; i < pl->npass; i++) {
@@ -516,6 +538,7 @@ int32_t ntt_run(uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t 
         src = dst;
         log_s += pl->deg[i];
     }
+    TRY(ws_leave(s));
     return B200ZK_OK;
 }
 
@@ -754,6 +777,8 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int32_t generator_dev(uint32_t** out, cudaStream_t s) { return get_generator_dev(out, s); }
 static std::vector<void (*)()> g_hooks;
 void on_shutdown(void (*fn)()) { g_hooks.push_back(fn); }
+int32_t ws_enter(cudaStream_t s) { return ::ws_enter(s); }
+int32_t ws_leave(cudaStream_t s) { return ::ws_leave(s); }
 }  // namespace b200zk_ctx
 
 // ==========================================================================================
@@ -810,6 +835,8 @@ int32_t b200zk_shutdown(void) {
                      &g.scan_tmp[0], &g.scan_tmp[1], &g.out_mont, &g.out_canon, &g.stage, &g.flag, &g.ntt_data,
                      &g.ntt_tmp[0], &g.ntt_tmp[1], &g.small};
     for (DevBuf* b : all) b->release();
+    if (g.ws_event) { cudaEventDestroy(g.ws_event); g.ws_event = nullptr; }
+    g.ws_used = false;
     if (g.stream) cudaStreamDestroy(g.stream);
     g.stream = nullptr;
     g.inited = false;

@@ -88,6 +88,19 @@ int32_t upload_fr(const uint8_t* v, uint32_t count, cudaStream_t s, uint32_t** o
     return B200ZK_OK;
 }
 
+// brackets an entry point's use of the shared scratch buffers / scalar ring (ctx.hpp)
+struct WsGuard {
+    cudaStream_t s;
+    bool active = false;
+    int32_t enter(cudaStream_t st) {
+        s = st;
+        int32_t rc = ctx::ws_enter(st);
+        active = rc == B200ZK_OK;
+        return rc;
+    }
+    ~WsGuard() { if (active) ctx::ws_leave(s); }
+};
+
 bool misaligned(const void* a, const void* b = nullptr, const void* c = nullptr, const void* d = nullptr) {
     return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) != 0;
 }
@@ -196,6 +209,8 @@ int32_t b200zk_g1_decompress_batch(const uint8_t* compressed, uint64_t n, uint8_
 int32_t b200zk_g1_fixed_mul_dev(const void* d_scalars, uint32_t scalar_fmt, uint64_t n, void* d_out_mont, void* stream) {
     std::lock_guard<std::mutex> lk(ctx::mutex());
     XTRY(enter());
+    WsGuard ws;
+    XTRY(ws.enter(S(stream)));
     if (n == 0) return B200ZK_OK;
     if (!d_scalars || !d_out_mont) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (scalar_fmt > B200ZK_FMT_MONT) return ctx::fail(B200ZK_ERR_INVALID_ARG, "unknown scalar format");
@@ -210,6 +225,8 @@ int32_t b200zk_srs_generate_dev(const uint8_t s_bytes[32], uint32_t k, const uin
                                 void* d_g_lagrange_mont, void* stream) {
     std::lock_guard<std::mutex> lk(ctx::mutex());
     XTRY(enter());
+    WsGuard ws;
+    XTRY(ws.enter(S(stream)));
     if (!s_bytes || (!d_g_mont && !d_g_lagrange_mont) || (d_g_lagrange_mont && !omega)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (k > 28) return ctx::fail(B200ZK_ERR_INVALID_ARG, "srs: k > 28 is not supported");
     if (misaligned(d_g_mont, d_g_lagrange_mont)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
@@ -287,6 +304,8 @@ int32_t b200zk_fr_convert_dev(const void* d_in, void* d_out, uint64_t n, uint32_
 int32_t b200zk_fr_power_table_dev(const uint8_t base[32], uint64_t row0, uint64_t rows, uint64_t cols, void* d_out, void* stream) {
     std::lock_guard<std::mutex> lk(ctx::mutex());
     XTRY(enter());
+    WsGuard ws;
+    XTRY(ws.enter(S(stream)));
     if (rows == 0 || cols == 0) return B200ZK_OK;
     if (!base || !d_out) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (misaligned(d_out)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
@@ -315,6 +334,8 @@ int32_t b200zk_fr_pointwise_dev(uint32_t op, const void* d_a, const void* d_b, c
                                 void* stream) {
     std::lock_guard<std::mutex> lk(ctx::mutex());
     XTRY(enter());
+    WsGuard ws;
+    XTRY(ws.enter(S(stream)));
     if (op > 4) return ctx::fail(B200ZK_ERR_INVALID_ARG, "pointwise: unknown op");
     if (n == 0) return B200ZK_OK;
     if (!d_a || !d_out || (op != 3 && !d_b) || (op == 3 && !scalar)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
@@ -329,6 +350,8 @@ int32_t b200zk_fr_pointwise_dev(uint32_t op, const void* d_a, const void* d_b, c
 int32_t b200zk_fr_lincomb_dev(const void* const* d_polys, const uint8_t* coeffs, uint32_t count, void* d_out, uint64_t n, void* stream) {
     std::lock_guard<std::mutex> lk(ctx::mutex());
     XTRY(enter());
+    WsGuard ws;
+    XTRY(ws.enter(S(stream)));
     if (!d_out && n) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (n == 0) return B200ZK_OK;
     if (count == 0) { XCU(cudaMemsetAsync(d_out, 0, n * 32, S(stream))); return B200ZK_OK; }
@@ -353,6 +376,8 @@ int32_t b200zk_fr_lincomb_dev(const void* const* d_polys, const uint8_t* coeffs,
 int32_t b200zk_fr_batch_invert_dev(const void* d_in, void* d_out, uint64_t n, void* stream) {
     std::lock_guard<std::mutex> lk(ctx::mutex());
     XTRY(enter());
+    WsGuard ws;
+    XTRY(ws.enter(S(stream)));
     if (n == 0) return B200ZK_OK;
     if (!d_in || !d_out) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (misaligned(d_in, d_out)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
@@ -363,6 +388,8 @@ int32_t b200zk_fr_running_product_dev(const void* d_in, void* d_out, uint64_t n,
                                       void* stream) {
     std::lock_guard<std::mutex> lk(ctx::mutex());
     XTRY(enter());
+    WsGuard ws;
+    XTRY(ws.enter(S(stream)));
     if (n == 0) return B200ZK_OK;
     if (!d_in || !d_out) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (misaligned(d_in, d_out)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
@@ -383,6 +410,8 @@ int32_t b200zk_fr_running_product_dev(const void* d_in, void* d_out, uint64_t n,
 int32_t b200zk_fr_kate_div_dev(const void* d_coeffs, uint64_t n, const uint8_t z[32], void* d_quot, void* d_eval, void* stream) {
     std::lock_guard<std::mutex> lk(ctx::mutex());
     XTRY(enter());
+    WsGuard ws;
+    XTRY(ws.enter(S(stream)));
     if (!z || (!d_coeffs && n) || (!d_quot && !d_eval)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (misaligned(d_coeffs, d_quot, d_eval)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
     cudaStream_t s = S(stream);
@@ -477,6 +506,8 @@ int32_t b200zk_gate_program_set_const(uint64_t handle, uint32_t index, const uin
 int32_t b200zk_gate_program_run_dev(uint64_t handle, const void* const* d_columns, void* d_out, uint32_t accumulate, void* stream) {
     std::lock_guard<std::mutex> lk(ctx::mutex());
     XTRY(enter());
+    WsGuard ws;
+    XTRY(ws.enter(S(stream)));
     auto it = x.programs.find(handle);
     if (it == x.programs.end()) return ctx::fail(B200ZK_ERR_BAD_HANDLE, "unknown gate-program handle");
     const GateProgram& gp = it->second;

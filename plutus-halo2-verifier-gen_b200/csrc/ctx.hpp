@@ -19,6 +19,9 @@ int sm_count();
 void count_launch();                                  // b200zk_launch_count()
 int32_t generator_dev(uint32_t** out, cudaStream_t s);// Montgomery affine generator of G1 in HBM
 void on_shutdown(void (*fn)());                       // called by b200zk_shutdown before the stream dies
+// cross-stream ordering of the process-wide workspaces: bracket every use of a shared scratch buffer
+int32_t ws_enter(cudaStream_t s);
+int32_t ws_leave(cudaStream_t s);
 }  // namespace b200zk_ctx
 
 #define XCU(call)                                                                                       \

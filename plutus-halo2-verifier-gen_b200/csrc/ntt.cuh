@@ -141,7 +141,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     // ---- load: element (ul, j) <- x[poly*n + u + j*(n/R)], ul fastest so consecutive lanes read
     //      consecutive u.  The plain path (no scaling) is unrolled so that the eight loads are in flight together;
     //      the scaled paths keep one copy of the product (code size: the kernel must stay in the instruction cache)
-    if (!a.in_scale && !a.reduce_in) {
+    if (!a.in_scale) {
 #pragma unroll
         for (int t = 0; t < 8; t++) {
             uint32_t idx = tid + t * NTT_THREADS;
@@ -151,6 +151,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
             if (col < a.total_cols) {
                 uint64_t poly = col >> a.log_cols, u = col & cmask;
                 v = ntt_ld(a.in + 8 * ((poly << a.log_n) + u + ((uint64_t)j << a.log_cols)));
+                if (a.reduce_in) fe_reduce_loose(v);
             }
             ntt_sts(sm, (ul << deg) | j, v);
         }

@@ -371,3 +371,29 @@ def test_large_input_sort_paths(gpu, oracle, dist):
     sc = uni.tobytes()
     assert msm(gpu, h, sc, n) == oracle.msm(pts, sc, n)
     gpu.capi.check(gpu.lib().b200zk_bases_release(h))
+
+
+def test_calls_on_different_streams_do_not_race(gpu, oracle):
+    """The workspaces are shared by all calls of the process: back-to-back device-side calls on two different CUDA
+    streams, never synchronised in between, must still give the single-stream results (the library orders them)."""
+    import ctypes as C
+    import torch
+    lib, chk = gpu.lib(), gpu.capi.check
+    n = 1 << 14
+    bases = oracle.synth_bases(0xB200, 0, n)
+    h = C.c_uint64(0)
+    chk(lib.b200zk_bases_register(gpu.capi.addr(bases), n, gpu.FMT_CANONICAL, 96, C.byref(h)))
+    sets = [oracle.synth_scalars(50 + i, 0, n) for i in range(4)]
+    want = [oracle.msm(bases, s, n) for s in sets]
+    d_sc = [torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda() for s in sets]
+    d_out = [torch.zeros(96, dtype=torch.uint8, device="cuda") for _ in sets]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i in range(4):
+            st = streams[i & 1]
+            chk(lib.b200zk_msm_g1_dev(h.value, 0, d_sc[i].data_ptr(), n, 1, 0, 0, d_out[i].data_ptr(), st.cuda_stream))
+        torch.cuda.synchronize()
+        for i in range(4):
+            assert bytes(d_out[i].cpu().numpy()) == want[i], (rep, i)
+    chk(lib.b200zk_bases_release(h.value))
