@@ -361,6 +361,9 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
         if (serial)
             LAUNCH(msm_reduce_kernel, (unsigned)((groups + 63) / 64), 64, 0, s, S_in, A_in, S_out, A_out, m, m_out,
                    (uint32_t)nwin, scale_log);
+        else if (groups <= 600)
+            // top of the tree: one CTA per group, 8 lanes per node, additions in 4 product levels instead of 14 products
+            LAUNCH(msm_reduce_coop8_kernel, (unsigned)groups, 256, 0, s, S_in, A_in, S_out, A_out, m, m_out, (uint32_t)nwin, scale_log);
         else
             LAUNCH(msm_reduce_coop_kernel, (unsigned)((groups + 3) / 4), 128, 0, s, S_in, A_in, S_out, A_out, m, m_out,
                    (uint32_t)nwin, scale_log);

@@ -469,26 +469,31 @@ __global__ void __launch_bounds__(128) msm_reduce_coop_kernel(const uint32_t* __
 // hold the same point and the independent products of each level of the formula run on different lanes,
 // then are broadcast: 3 product levels per doubling, 4 per full addition.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ Fp fp_bcast(const Fp& v, int src) {
+// W lanes (32: a whole warp, 8: an aligned eighth of one) hold the same point
+template <int W> __device__ __forceinline__ uint32_t coop_mask() {
+    return W == 32 ? 0xffffffffu : (0xffu << ((threadIdx.x & 31u) & ~7u));
+}
+template <int W> __device__ __forceinline__ Fp fp_bcast(const Fp& v, int src) {
     Fp r;
+    const uint32_t m = coop_mask<W>();
 #pragma unroll
-    for (int k = 0; k < 12; k++) r.l[k] = __shfl_sync(0xffffffffu, v.l[k], src);
+    for (int k = 0; k < 12; k++) r.l[k] = __shfl_sync(m, v.l[k], src, W);
     return r;
 }
 __device__ __forceinline__ void fp_pick(Fp& dst, const Fp& v, bool take) {
 #pragma unroll
     for (int k = 0; k < 12; k++) dst.l[k] = take ? v.l[k] : dst.l[k];
 }
-// all lanes must call these with identical (replicated) arguments
-__device__ __noinline__ void warp_xyzz_dbl(G1Xyzz& a) {
+// all W lanes of a group must call these with identical (replicated) arguments
+template <int W> __device__ __noinline__ void coop_xyzz_dbl(G1Xyzz& a) {
     if (xyzz_is_inf(a)) return;
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & (W - 1);
     Fp u = fe_dbl(a.y);
     // level 1: V = U^2 (lane 0), X^2 (lane 1)
     Fp o = u;
     fp_pick(o, a.x, lane == 1);
     Fp t = fp_mul_call(o, o);
-    Fp v = fp_bcast(t, 0), xx = fp_bcast(t, 1);
+    Fp v = fp_bcast<W>(t, 0), xx = fp_bcast<W>(t, 1);
     Fp m = fe_add(fe_dbl(xx), xx);
     // level 2: W = U*V (0), S = X*V (1), M^2 (2), ZZ3 = V*ZZ (3)
     Fp p = u, q = v;
@@ -497,7 +502,7 @@ __device__ __noinline__ void warp_xyzz_dbl(G1Xyzz& a) {
     fp_pick(q, m, lane == 2);
     fp_pick(p, a.zz, lane == 3);
     t = fp_mul_call(p, q);
-    Fp w = fp_bcast(t, 0), sx = fp_bcast(t, 1), mm = fp_bcast(t, 2), zz3 = fp_bcast(t, 3);
+    Fp w = fp_bcast<W>(t, 0), sx = fp_bcast<W>(t, 1), mm = fp_bcast<W>(t, 2), zz3 = fp_bcast<W>(t, 3);
     Fp x3 = fe_sub(fe_sub(mm, sx), sx);
     // level 3: M*(S - X3) (0), W*Y (1), ZZZ3 = W*ZZZ (2)
     p = m; q = fe_sub(sx, x3);
@@ -505,16 +510,16 @@ __device__ __noinline__ void warp_xyzz_dbl(G1Xyzz& a) {
     fp_pick(q, a.y, lane == 1);
     fp_pick(q, a.zzz, lane == 2);
     t = fp_mul_call(p, q);
-    Fp y3 = fe_sub(fp_bcast(t, 0), fp_bcast(t, 1));
-    a.zzz = fp_bcast(t, 2);
+    Fp y3 = fe_sub(fp_bcast<W>(t, 0), fp_bcast<W>(t, 1));
+    a.zzz = fp_bcast<W>(t, 2);
     a.zz = zz3;
     a.x = x3;
     a.y = y3;
 }
-__device__ __noinline__ void warp_xyzz_add(G1Xyzz& a, const G1Xyzz& b) {
+template <int W> __device__ __noinline__ void coop_xyzz_add(G1Xyzz& a, const G1Xyzz& b) {
     if (xyzz_is_inf(b)) return;
     if (xyzz_is_inf(a)) { a = b; return; }
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & (W - 1);
     // level 1: U1 = X1*ZZ2 (0), U2 = X2*ZZ1 (1), S1 = Y1*ZZZ2 (2), S2 = Y2*ZZZ1 (3), ZZ1*ZZ2 (4), ZZZ1*ZZZ2 (5)
     Fp p = a.x, q = b.zz;
     fp_pick(p, b.x, lane == 1);   fp_pick(q, a.zz, lane == 1);
@@ -523,10 +528,11 @@ __device__ __noinline__ void warp_xyzz_add(G1Xyzz& a, const G1Xyzz& b) {
     fp_pick(p, a.zz, lane == 4);
     fp_pick(p, a.zzz, lane == 5); fp_pick(q, b.zzz, lane == 5);
     Fp t = fp_mul_call(p, q);
-    Fp u1 = fp_bcast(t, 0), u2 = fp_bcast(t, 1), s1 = fp_bcast(t, 2), s2 = fp_bcast(t, 3), zz12 = fp_bcast(t, 4), zzz12 = fp_bcast(t, 5);
+    Fp u1 = fp_bcast<W>(t, 0), u2 = fp_bcast<W>(t, 1), s1 = fp_bcast<W>(t, 2), s2 = fp_bcast<W>(t, 3), zz12 = fp_bcast<W>(t, 4),
+       zzz12 = fp_bcast<W>(t, 5);
     Fp pp_ = fe_sub(u2, u1), r = fe_sub(s2, s1);
     if (fe_is_zero(pp_)) {
-        if (fe_is_zero(r)) warp_xyzz_dbl(a);
+        if (fe_is_zero(r)) coop_xyzz_dbl<W>(a);
         else xyzz_set_inf(a);
         return;
     }
@@ -534,13 +540,13 @@ __device__ __noinline__ void warp_xyzz_add(G1Xyzz& a, const G1Xyzz& b) {
     p = pp_;
     fp_pick(p, r, lane == 1);
     t = fp_mul_call(p, p);
-    Fp pp = fp_bcast(t, 0), rr = fp_bcast(t, 1);
+    Fp pp = fp_bcast<W>(t, 0), rr = fp_bcast<W>(t, 1);
     // level 3: PPP = P*PP (0), Q = U1*PP (1), ZZ3 = ZZ12*PP (2)
     p = pp_;
     fp_pick(p, u1, lane == 1);
     fp_pick(p, zz12, lane == 2);
     t = fp_mul_call(p, pp);
-    Fp ppp = fp_bcast(t, 0), qq = fp_bcast(t, 1), zz3 = fp_bcast(t, 2);
+    Fp ppp = fp_bcast<W>(t, 0), qq = fp_bcast<W>(t, 1), zz3 = fp_bcast<W>(t, 2);
     Fp x3 = fe_sub(fe_sub(fe_sub(rr, ppp), qq), qq);
     // level 4: R*(Q - X3) (0), S1*PPP (1), ZZZ3 = ZZZ12*PPP (2)
     p = r; q = fe_sub(qq, x3);
@@ -548,10 +554,83 @@ __device__ __noinline__ void warp_xyzz_add(G1Xyzz& a, const G1Xyzz& b) {
     fp_pick(p, zzz12, lane == 2);
     fp_pick(q, ppp, lane >= 1);
     t = fp_mul_call(p, q);
-    a.y = fe_sub(fp_bcast(t, 0), fp_bcast(t, 1));
-    a.zzz = fp_bcast(t, 2);
+    a.y = fe_sub(fp_bcast<W>(t, 0), fp_bcast<W>(t, 1));
+    a.zzz = fp_bcast<W>(t, 2);
     a.zz = zz3;
     a.x = x3;
+}
+__device__ __forceinline__ void warp_xyzz_dbl(G1Xyzz& a) { coop_xyzz_dbl<32>(a); }
+__device__ __forceinline__ void warp_xyzz_add(G1Xyzz& a, const G1Xyzz& b) { coop_xyzz_add<32>(a, b); }
+
+// ---------------------------------------------------------------------------------------
+// 7b. the same bucket-reduction recurrence for the top levels of the tree, where the machine is nearly empty
+//   (<= a few hundred groups): one CTA per group of 32 nodes, 8 lanes per node; the 15 dependent additions of the
+//   scan / butterflies each take 4 product levels (coop_xyzz_add<8>) instead of 14 serial products, the 2^scale_log
+//   doublings 3 instead of 9.  Nodes are exchanged through shared memory.  Measured at 2^20 points: the last two
+//   levels 0.33 + 0.40 ms -> 0.20 + 0.21 ms.  (Level 0 is throughput-bound -- two full additions per bucket -- and a
+//   two-lanes-per-group variant of it that halves the dependent chain was measured 10 % slower; removed.)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) msm_reduce_coop8_kernel(const uint32_t* __restrict__ S_in, const uint32_t* __restrict__ A_in,
+                                                               uint32_t* __restrict__ S_out, uint32_t* __restrict__ A_out,
+                                                               uint32_t m_in, uint32_t m_out, uint32_t nwin, uint32_t scale_log) {
+    __shared__ uint32_t sh[32][48];
+    const uint32_t grp = blockIdx.x, node = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    const uint32_t w = grp / m_out, g = grp % m_out;
+    const uint64_t base = (uint64_t)w * m_in + (uint64_t)g * COOP_RADIX;
+    const uint32_t cnt = min((uint32_t)COOP_RADIX, m_in - g * COOP_RADIX);
+    auto put = [&](const G1Xyzz& v) {                       // the node's 8 lanes write 6 words each
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            uint32_t idx = sub * 6 + k;
+            uint32_t val = idx < 12 ? v.x.l[idx] : idx < 24 ? v.y.l[idx - 12] : idx < 36 ? v.zz.l[idx - 24] : v.zzz.l[idx - 36];
+            sh[node][idx] = val;
+        }
+    };
+    auto get = [&](uint32_t n) { return xyzz_ld_gen(&sh[n][0]); };
+    G1Xyzz run;
+    if (node < cnt) run = xyzz_ld(S_in, base + node);
+    else xyzz_set_inf(run);
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {                      // run_i = sum_{i' >= i} S_i'
+        put(run);
+        __syncthreads();
+        G1Xyzz o;
+        if (node + d < 32) o = get(node + d);
+        else xyzz_set_inf(o);
+        __syncthreads();
+        coop_xyzz_add<8>(run, o);
+    }
+    G1Xyzz T;                                               // T = sum_{i >= 1} run_i = sum_i i * S_i
+    if (node >= 1) T = run;
+    else xyzz_set_inf(T);
+    G1Xyzz asum;
+    if (A_in) {
+        if (node < cnt) asum = xyzz_ld(A_in, base + node);
+        else xyzz_set_inf(asum);
+    } else asum = run;                                      // level 0: A_i = S_i, node 0 holds their sum
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        put(T);
+        __syncthreads();
+        G1Xyzz o = get(node ^ d);
+        __syncthreads();
+        coop_xyzz_add<8>(T, o);
+        if (A_in) {
+            put(asum);
+            __syncthreads();
+            G1Xyzz oa = get(node ^ d);
+            __syncthreads();
+            coop_xyzz_add<8>(asum, oa);
+        }
+    }
+    if (node == 0) {
+        for (uint32_t k = 0; k < scale_log; k++) coop_xyzz_dbl<8>(T);
+        coop_xyzz_add<8>(asum, T);
+        if (sub == 0) {
+            xyzz_st(S_out, (uint64_t)w * m_out + g, run);
+            xyzz_st(A_out, (uint64_t)w * m_out + g, asum);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
