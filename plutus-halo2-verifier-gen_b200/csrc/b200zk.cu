@@ -286,10 +286,25 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     const uint32_t fmt_mont = scalar_fmt == B200ZK_FMT_MONT ? 1u : 0u;
     // (A two-pass sort -- coarse bins of 2048 buckets staged through shared memory, then one CTA per bin --
     // was built and measured at 2^24: 11.0 ms against 7.9 ms for this one-pass histogram + scatter; removed.)
-    LAUNCH(msm_digits_kernel<0>, dgrid, 256, 0, s, d_scalars, n, fmt_mont, pl, counts, (uint32_t*)nullptr);
+    LAUNCH(msm_digits_kernel<0>, dgrid, 256, 0, s, d_scalars, n, fmt_mont, pl, counts, (uint32_t*)nullptr, 0u, 0xffffffffu, (const uint32_t*)nullptr, 0u);
     TRY(scan_u32(counts, offsets, NBt + 1, 0, s));
     CU(cudaMemcpyAsync(cursor, offsets, (NBt + 1) * 4, cudaMemcpyDeviceToDevice, s));
-    LAUNCH(msm_digits_kernel<1>, dgrid, 256, 0, s, d_scalars, n, fmt_mont, pl, cursor, entries);
+    {
+        // The scatter writes 4-byte entries into bucket lists that are spread over the whole entry array.  When that
+        // array is much larger than L2, the 32-byte sector a list is currently filling is evicted half full and read
+        // back (DRAM read-modify-write).  Scattering one bucket range at a time keeps the open sectors (32 B per bucket
+        // of the range) resident; the scalars are re-read and re-coded once per pass, which is cheap.
+        static int passes_env = -1;
+        if (passes_env < 0) { const char* v = getenv("B200ZK_SCATTER_PASSES"); passes_env = v ? atoi(v) : 0; }
+        uint32_t passes = 1;
+        if (passes_env > 0) passes = (uint32_t)passes_env;
+        else if (NBt * 32 >= (48ull << 20)) passes = 2;   // measured at 2^24 (2^21 buckets): 1 pass 8.98 ms, 2 passes 7.44, 4 passes 9.22 (each pass re-codes every scalar)
+        for (uint32_t ps = 0; ps < passes; ps++) {
+            uint32_t lo = (uint32_t)(NBt * ps / passes), hi = (uint32_t)(NBt * (ps + 1) / passes);
+            LAUNCH(msm_digits_kernel<1>, dgrid, 256, 0, s, d_scalars, n, fmt_mont, pl, cursor, entries, lo, hi,
+                   passes > 1 ? (const uint32_t*)(offsets + NBt) : (const uint32_t*)nullptr, 100u << 20);
+        }
+    }
     unsigned bgrid = (unsigned)((NBt + 255) / 256);
     LAUNCH(msm_task_count_kernel, bgrid, 256, 0, s, (const uint32_t*)counts, NBt, pl.smax, ntask);
     TRY(scan_u32(ntask, task_off, NBt + 1, 0, s));
@@ -352,7 +367,9 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     int pp = 0;
     const uint32_t* win_sums = nullptr;
     do {
-        bool serial = (uint64_t)((m + RED_RADIX - 1) / RED_RADIX) * nwin >= 32768;
+        // serial groups while there are >= 4096 of them: at 2^24 the second level (8192 groups) takes 0.5 ms serially
+        // against 1.5 ms for 4096 warp-cooperative groups (1.7 waves of a latency-bound kernel)
+        bool serial = (uint64_t)((m + RED_RADIX - 1) / RED_RADIX) * nwin >= 4096;
         uint32_t radix = serial ? RED_RADIX : COOP_RADIX;
         uint32_t m_out = (m + radix - 1) / radix;
         uint32_t* S_out = g.redS[pp].as<uint32_t>();

@@ -69,7 +69,16 @@ __device__ __forceinline__ int32_t msm_digit(const uint32_t s[9], uint32_t w, ui
 template <int MODE>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, uint32_t fmt_mont,
                                                          MsmPlan pl, uint32_t* __restrict__ counts_or_cursor,
-                                                         uint32_t* __restrict__ entries) {
+                                                         uint32_t* __restrict__ entries, uint32_t g_lo, uint32_t g_hi,
+                                                         const uint32_t* __restrict__ total_entries, uint32_t split_min) {
+    // Range passes only pay when the entry array is far larger than L2 (uniform scalars); with few entries (skewed
+    // prover columns) the first pass takes the whole range and the others leave at once.  The count is on the device.
+    if (MODE == 1 && total_entries) {
+        if (*total_entries < split_min) {
+            if (g_lo != 0) return;
+            g_hi = 0xffffffffu;
+        }
+    }
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
     const uint32_t b = blockIdx.y;             // batch item: its own scalar vector and bucket sets
@@ -86,7 +95,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint32_t* __restr
         uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
         // with precomputed rows every window feeds the same bucket set and the entry names the row
         uint32_t g = pl.precomp ? b * pl.nb + mag - 1 : (b * pl.W + w) * pl.nb + mag - 1;
-        bool valid = live && d != 0;
+        bool valid = live && d != 0 && g >= g_lo && g < g_hi;   // [g_lo, g_hi): the bucket range of this scatter pass
         uint32_t key = valid ? g : (0xffffffe0u + lane);          // invalid lanes get private keys
         uint32_t peers = __match_any_sync(0xffffffffu, key);
         uint32_t leader = __ffs(peers) - 1, cnt = __popc(peers), rank = __popc(peers & ((1u << lane) - 1));

@@ -110,7 +110,7 @@ def test_edge_points(gpu, oracle, pyref):
         gpu.capi.check(gpu.lib().b200zk_bases_release(hh))
 
 
-@pytest.mark.parametrize("variant", [3, 4, 5])
+@pytest.mark.parametrize("variant", [3, 4, 5, 6])
 def test_edge_cases_every_accumulate_path(gpu, oracle, pyref, variant):
     """repeated / opposite / identity points and all-equal scalars through the XYZZ path (3) and the
     batched-affine paths (4, 5), with buckets long enough for several affine rounds"""
@@ -171,7 +171,7 @@ def test_all_window_sizes_and_task_splits(gpu, oracle, table, c, smax, tables):
         h = register(gpu, pts, n, fmt=0 if tables else NO_TABLES)
         assert msm(gpu, h, sc, n) == exp
         assert msm(gpu, h, sc[32 * 100:], n - 500, offset=100) == oracle.msm(pts[96 * 100:], sc[32 * 100:], n - 500)
-        for variant in range(6):
+        for variant in range(7):
             gpu.capi.check(gpu.lib().b200zk_set_msm_tuning(c | ((variant + 1) << 8), smax))
             assert msm(gpu, h, sc, n) == exp, variant
         gpu.capi.check(gpu.lib().b200zk_bases_release(h))
