@@ -368,10 +368,10 @@ def main():
                                  "(CUDA events on the launching stream, last timed step, max over ranks); peak = IMAD.WIDE.U32 "
                                  "micro-benchmark measured in this run; window bits actually used: %s"
                                  % (LMAC_PER_POINT, n_local, prof.get("window_bits")),
-                         "issued_imad_wide_frac": (2756.0 * n_local * (prof.get("windows") or 0) / (acc_ms * 1e-3)) / imad_peak
+                         "issued_imad_wide_frac": (2611.0 * n_local * (prof.get("windows") or 0) / (acc_ms * 1e-3)) / imad_peak
                          if (acc_ms and imad_peak) else None,
-                         "issued_note": "IMAD.WIDE actually issued by the kernel (8 products x 289 + 2 squarings x 222 per mixed "
-                                        "addition, one addition per point and table row) / time / peak: the pipe utilisation; "
+                         "issued_note": "IMAD.WIDE actually issued by the kernel (6 products x 289 + 2 squarings x 222 + one fused pair of products "
+                                        "x 433 per mixed addition, one addition per point and table row) / time / peak: the pipe utilisation; "
                                         "`frac` above uses the fixed 16-window accounting of SURVEY 8d and exceeds it when window "
                                         "tables allow fewer rows",
                          "phases_ms": {k: prof.get(k) for k in ("sort", "accumulate", "tail")},

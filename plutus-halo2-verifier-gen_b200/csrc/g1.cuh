@@ -27,6 +27,7 @@ struct G1Xyzz {
 struct MulInline {
     static HD Fp mul(const Fp& a, const Fp& b) { return fe_mul(a, b); }
     static HD Fp sqr(const Fp& a) { return fe_mul(a, a); }
+    static HD Fp mulsub(const Fp& a, const Fp& b, const Fp& c, const Fp& d) { return fe_sub(fe_mul(a, b), fe_mul(c, d)); }
 };
 
 HD bool g1a_is_inf(const G1Affine& a) { return fe_is_zero(a.x) && fe_is_zero(a.y); }

@@ -48,6 +48,15 @@ template <class P> static int check_field(const char* name,
         if (!fe_eq(r, e)) { bad++; if (bad < 5) printf("%s mul mismatch it=%d\n", name, it); }
         r = fe_from_mont(fe_sqr_fast(am)); omul((uint8_t*)a.l, (uint8_t*)a.l, (uint8_t*)e.l);
         if (!fe_eq(r, e) || !fe_eq(fe_sqr_fast(am), fe_mul(am, am))) { bad++; if (bad < 5) printf("%s sqr_fast mismatch it=%d\n", name, it); }
+        if constexpr (P::N == 12) {   // a*b + c*d in one pass (Fp only: needs three bits of headroom), against the two-product formulation (also with both products at their maximum)
+            Fe<P> cm = fe_to_mont(rnd_canon<P>()), dm = fe_to_mont(rnd_canon<P>());
+            if (it == 1) { cm = am; dm = am; }
+            Fe<P> want = fe_add(fe_mul(am, bm), fe_mul(cm, dm));
+            if (!fe_eq(fe_mul2(am, bm, cm, dm), want)) { bad++; if (bad < 5) printf("%s mul2 mismatch it=%d\n", name, it); }
+            // raw maximal operands (all limbs p-1 pattern, not Montgomery-converted): stresses the accumulator bound
+            Fe<P> mx; for (int i = 0; i < P::N; i++) mx.l[i] = P::p(i); mx.l[0] -= 1;
+            if (it < 4 && !fe_eq(fe_mul2(mx, mx, mx, mx), fe_add(fe_mul(mx, mx), fe_mul(mx, mx)))) { bad++; printf("%s mul2 max mismatch\n", name); }
+        }
         r = fe_from_mont(fe_add(am, bm)); oadd((uint8_t*)a.l, (uint8_t*)b.l, (uint8_t*)e.l);
         if (!fe_eq(r, e)) { bad++; if (bad < 5) printf("%s add mismatch it=%d\n", name, it); }
         r = fe_from_mont(fe_sub(am, bm)); osub((uint8_t*)a.l, (uint8_t*)b.l, (uint8_t*)e.l);
