@@ -336,6 +336,7 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
         switch (g.tune_variant) {
             case 1: LAUNCH(msm_accumulate_kernel_v1, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
             case 2: LAUNCH(msm_accumulate_kernel_v2, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
+            case 7: LAUNCH(msm_accumulate_kernel_v7, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
             case 6: LAUNCH(msm_accumulate_kernel_v6, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
             case 3: LAUNCH(msm_accumulate_kernel_v3, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
             case 4:
@@ -522,6 +523,8 @@ int32_t ntt_run(uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t 
         CU(cudaFuncSetAttribute(ntt_pass_kernel_occ2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
         CU(cudaFuncSetAttribute(ntt_pass_kernel_call2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
         CU(cudaFuncSetAttribute(ntt_pass_kernel_call3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+        CU(cudaFuncSetAttribute(ntt_pass_kernel_plain2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+        CU(cudaFuncSetAttribute(ntt_pass_kernel_wl2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
         if (const char* v = getenv("B200ZK_NTT_VARIANT")) ntt_variant = atoi(v);
         attr_set = true;
     }
@@ -553,6 +556,8 @@ int32_t ntt_run(uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t 
         if (ntt_variant == 0) LAUNCH(ntt_pass_kernel, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         else if (ntt_variant == 2) LAUNCH(ntt_pass_kernel_call2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         else if (ntt_variant == 3) LAUNCH(ntt_pass_kernel_call3, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+        else if (ntt_variant == 4) LAUNCH(ntt_pass_kernel_plain2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+        else if (ntt_variant == 5) LAUNCH(ntt_pass_kernel_wl2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         else LAUNCH(ntt_pass_kernel_occ2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         TRY(prof_mark((int)i + 1, s));
         src = dst;

@@ -698,6 +698,10 @@ template <class P> HD Fe<P> fe_pow_u64(const Fe<P>& a, uint64_t e) {
     return acc;
 }
 
+// Fr with all eight m*r products on the multiplier pipe (experiment: is the NTT bound by the FMA or by the ALU pipe?)
+struct FrParamsPlain : FrParams {
+    static constexpr bool LOW_LIMBS_TRIVIAL = false;
+};
 typedef Fe<FpParams> Fp;
 typedef Fe<FrParams> Fr;
 

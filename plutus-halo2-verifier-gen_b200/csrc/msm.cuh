@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(128, 3) msm_accumulate_kernel_v1(MSM_ACC_ARGS)
 __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel_v2(MSM_ACC_ARGS) { msm_accumulate_body<2>(MSM_ACC_PASS); }
 __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel_v3(MSM_ACC_ARGS) { msm_accumulate_body<3>(MSM_ACC_PASS); }
 __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel_v6(MSM_ACC_ARGS) { msm_accumulate_body<6>(MSM_ACC_PASS); }
+__global__ void __launch_bounds__(128, 3) msm_accumulate_kernel_v7(MSM_ACC_ARGS) { msm_accumulate_body<6>(MSM_ACC_PASS); }   // experiment: 168 registers, 3 CTAs/SM
 
 // Variants 4/5: batched affine additions (affine_tree.cuh), one thread per task as above.
 __device__ __noinline__ Fp fp_inv_fast_call(Fp a) { return fe_inv_fast(a); }

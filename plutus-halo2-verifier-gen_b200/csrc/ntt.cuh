@@ -43,17 +43,23 @@ struct NttPassArgs {
     uint32_t reduce_in;       // canonical input may be >= r: reduce on read (transcript.ak:158-179)
 };
 
-__device__ __forceinline__ uint32_t ntt_pad(uint32_t e) { return e + (e >> 5); }
-
-__device__ __forceinline__ Fr ntt_lds(const uint32_t* sm, uint32_t e) {
+// Position of element e inside a word plane.  Layout 0: one pad word per 32 elements.  Layout 1 (WL): an XOR swizzle
+// that keeps every access pattern of the kernel conflict-free when the lower index bits are owned by single warps:
+// bank = e[4:0] ^ (e[7:5] << 2) ^ (e[10:8] << 2) ^ e[7:6]  (lanes may own any five of the bits 0..7, or bits 6..10 in
+// the bit-reversed store, and still hit 32 different banks).
+template <bool WL> __device__ __forceinline__ uint32_t ntt_pos(uint32_t e) {
+    if (WL) return e ^ ((((e >> 5) ^ (e >> 8)) & 7u) << 2) ^ ((e >> 6) & 3u);
+    return e + (e >> 5);
+}
+template <bool WL> __device__ __forceinline__ Fr ntt_lds(const uint32_t* sm, uint32_t e) {
     Fr r;
-    uint32_t pos = ntt_pad(e);
+    uint32_t pos = ntt_pos<WL>(e);
 #pragma unroll
     for (int w = 0; w < 8; w++) r.l[w] = sm[w * NTT_PLANE + pos];
     return r;
 }
-__device__ __forceinline__ void ntt_sts(uint32_t* sm, uint32_t e, const Fr& v) {
-    uint32_t pos = ntt_pad(e);
+template <bool WL> __device__ __forceinline__ void ntt_sts(uint32_t* sm, uint32_t e, const Fr& v) {
+    uint32_t pos = ntt_pos<WL>(e);
 #pragma unroll
     for (int w = 0; w < 8; w++) sm[w * NTT_PLANE + pos] = v.l[w];
 }
@@ -84,28 +90,50 @@ __device__ __noinline__ Fr fr_mul_call(Fr a, Fr b) { return fe_mul(a, b); }
 struct FrMulInline {
     static __device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) { return fe_mul(a, b); }
 };
+// experiment: every m*r product on the multiplier pipe (FrParamsPlain), same value as fe_mul on Fr
+struct FrMulPlain {
+    static __device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) {
+        Fe<FrParamsPlain> x, y;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { x.l[i] = a.l[i]; y.l[i] = b.l[i]; }
+        Fe<FrParamsPlain> z = fe_mul(x, y);
+        Fr r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.l[i] = z.l[i];
+        return r;
+    }
+};
 struct FrMulCall {
     static __device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) { return fr_mul_call(a, b); }
 };
 
 // radix-2 DIF stages on index bits lb+NB-1 .. lb of the CTA-local array; the thread owns the 8
 // elements whose index differs in bits lb..lb+2.
-template <int NB, class M>
+template <int NB, class M, bool WL>
 __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restrict__ tw_local, uint32_t deg,
                                           uint32_t lb, uint32_t tid) {
-    // lanes walk the low index bits when that is conflict-free (lb >= 5), else the high bits
-    uint32_t lo, hi;
-    if (lb >= 5) {
-        lo = tid & ((1u << lb) - 1);
-        hi = tid >> lb;
+    uint32_t base;
+    if (WL && lb + 2 <= 7) {
+        // warp-local: warp w owns elements [256 w, 256 w + 256); the lane supplies the five index bits of 0..7 that the
+        // thread does not iterate over.  No other warp touches this block until the final store.
+        const uint32_t lane = tid & 31, warp = tid >> 5;
+        const uint32_t lo = lane & ((1u << lb) - 1), hi = lane >> lb;
+        base = (warp << 8) | (hi << (lb + 3)) | lo;
     } else {
-        hi = tid & ((1u << (NTT_LOGB - 3 - lb)) - 1);
-        lo = tid >> (NTT_LOGB - 3 - lb);
+        // lanes walk the low index bits when that is conflict-free (lb >= 5), else the high bits
+        uint32_t lo, hi;
+        if (lb >= 5) {
+            lo = tid & ((1u << lb) - 1);
+            hi = tid >> lb;
+        } else {
+            hi = tid & ((1u << (NTT_LOGB - 3 - lb)) - 1);
+            lo = tid >> (NTT_LOGB - 3 - lb);
+        }
+        base = (hi << (lb + 3)) | lo;
     }
-    uint32_t base = (hi << (lb + 3)) | lo;
     Fr v[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) v[j] = ntt_lds(sm, base | ((uint32_t)j << lb));
+    for (int j = 0; j < 8; j++) v[j] = ntt_lds<WL>(sm, base | ((uint32_t)j << lb));
     uint32_t rmask = (1u << deg) - 1;
 #pragma unroll
     for (int q = NB - 1; q >= 0; q--) {
@@ -126,10 +154,10 @@ __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restri
         }
     }
 #pragma unroll
-    for (int j = 0; j < 8; j++) ntt_sts(sm, base | ((uint32_t)j << lb), v[j]);
+    for (int j = 0; j < 8; j++) ntt_sts<WL>(sm, base | ((uint32_t)j << lb), v[j]);
 }
 
-template <class M>
+template <class M, bool WL>
 __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     extern __shared__ uint32_t sm[];
     const uint32_t tid = threadIdx.x;
@@ -153,7 +181,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
                 v = ntt_ld(a.in + 8 * ((poly << a.log_n) + u + ((uint64_t)j << a.log_cols)));
                 if (a.reduce_in) fe_reduce_loose(v);
             }
-            ntt_sts(sm, (ul << deg) | j, v);
+            ntt_sts<WL>(sm, (ul << deg) | j, v);
         }
     } else
 #pragma unroll 1
@@ -169,7 +197,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
             if (a.reduce_in) fe_reduce_loose(v);
             if (a.in_scale) v = M::mul(v, ntt_ldg(a.in_scale + 8 * (u + ((uint64_t)j << a.log_cols))));
         }
-        ntt_sts(sm, (ul << deg) | j, v);
+        ntt_sts<WL>(sm, (ul << deg) | j, v);
     }
     __syncthreads();
 
@@ -178,11 +206,14 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     while (rem > 0) {
         int nb = rem >= 3 ? 3 : rem;
         uint32_t lb = (uint32_t)(rem - nb);
-        if (nb == 3) ntt_group<3, M>(sm, a.tw_local, deg, lb, tid);
-        else if (nb == 2) ntt_group<2, M>(sm, a.tw_local, deg, lb, tid);
-        else ntt_group<1, M>(sm, a.tw_local, deg, lb, tid);
-        __syncthreads();
+        if (nb == 3) ntt_group<3, M, WL>(sm, a.tw_local, deg, lb, tid);
+        else if (nb == 2) ntt_group<2, M, WL>(sm, a.tw_local, deg, lb, tid);
+        else ntt_group<1, M, WL>(sm, a.tw_local, deg, lb, tid);
         rem -= nb;
+        // the next sweep works on bits below lb: if both this sweep and the next stay inside a warp's 256-element block
+        // the warp only has to wait for itself
+        if (WL && rem > 0 && lb + 2 <= 7) __syncwarp();
+        else __syncthreads();
     }
 
     // ---- store: y[poly*n + q + s*(R*p + k)] = X_u[k] * T[p*R + k]; X_u[k] sits at bitrev(k).
@@ -198,7 +229,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
         if (col >= a.total_cols) continue;
         uint32_t kr = __brev(k) >> (32 - deg);
         if (deg == 0) kr = 0;
-        Fr v = ntt_lds(sm, (ul << deg) | kr);
+        Fr v = ntt_lds<WL>(sm, (ul << deg) | kr);
         uint64_t poly = col >> a.log_cols, u = col & cmask;
         uint64_t q = u & (((uint64_t)1 << a.log_s) - 1), p = u >> a.log_s;
         if (a.tw_pass) v = M::mul(v, ntt_ldg(a.tw_pass + 8 * ((p << deg) + k)));
@@ -210,10 +241,13 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
 }
 
 // one CTA per SM (registers unconstrained) and two CTAs per SM (<= 128 registers); the plan picks
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) { ntt_pass_body<FrMulInline>(a); }
-__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_occ2(NttPassArgs a) { ntt_pass_body<FrMulInline>(a); }
-__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_call2(NttPassArgs a) { ntt_pass_body<FrMulCall>(a); }
-__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel_call3(NttPassArgs a) { ntt_pass_body<FrMulCall>(a); }
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) { ntt_pass_body<FrMulInline, false>(a); }
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_occ2(NttPassArgs a) { ntt_pass_body<FrMulInline, false>(a); }
+// swizzled planes, warp-local sweeps on the index bits 0..7 (CTA barriers only around the sweeps that cross warps)
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_wl2(NttPassArgs a) { ntt_pass_body<FrMulInline, true>(a); }
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_call2(NttPassArgs a) { ntt_pass_body<FrMulCall, false>(a); }
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_plain2(NttPassArgs a) { ntt_pass_body<FrMulPlain, false>(a); }
+__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel_call3(NttPassArgs a) { ntt_pass_body<FrMulCall, false>(a); }
 
 // out[i] = scale * base^(e0 + i*mult mod 2^64), generic table generator (Montgomery form in and out).
 // kind 0: exponent = i * mult.  kind 1 (pass table): i = p*R + k, exponent = mult * p * k.

@@ -284,6 +284,14 @@ class DeviceBuffer:
             check(lib().b200zk_dev_free(self.ptr))
             self.ptr = None
 
+    def __del__(self):   # best effort: columns that go out of scope give their HBM back
+        try:
+            if getattr(self, "ptr", None):
+                lib().b200zk_dev_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
 
 class FrVec(DeviceBuffer):
     """n Fr elements in HBM, Montgomery form (the in-memory form of midnight_curves::Fq)."""
