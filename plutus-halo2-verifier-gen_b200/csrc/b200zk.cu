@@ -124,9 +124,12 @@ struct Ctx {
     MsmPlan last_plan{};
     // MSM workspace
     DevBuf scalars, counts, offsets, cursor, ntask, task_off, entries, task_bucket, task_start, task_len, buckets,
-        partials, len_hist, len_off, order, heavy, heavy_items, adhoc, aff_a, aff_b, aff_pre, redS[2], redA[2], scan_tmp[2], out_mont, out_canon, stage, flag;
+        partials, len_hist, len_off, order, heavy, heavy_items, adhoc, buckets2, aff_a, aff_b, aff_pre, redS[2], redA[2], scan_tmp[2], out_mont, out_canon, stage, flag;
     // NTT workspace
     DevBuf ntt_data, ntt_tmp[2], small;
+    // second stream + events for host-buffer MSMs that stream their scalars in two halves
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev[2] = {nullptr, nullptr};
     // cross-stream ordering of the shared workspaces
     cudaEvent_t ws_event = nullptr;
     cudaStream_t ws_stream = nullptr;
@@ -227,16 +230,23 @@ MsmPlan msm_plan(uint64_t n, uint32_t batch, const BaseTable* tab) {
 }
 
 // d_scalars: batch*n Fr (device).  d_bases: n packed Montgomery affine points.
+// One chunk of a scalar vector that arrives in pieces (host-buffer MSMs): n_total fixes the plan, i0 is the index of the
+// chunk's first point, the first chunk owns g.buckets, later chunks accumulate into g.buckets2 and are folded in, the
+// last chunk runs the tail.
+struct MsmChunk {
+    uint64_t n_total, i0;
+    bool first, last;
+};
 int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, uint32_t batch,
                 uint32_t scalar_fmt, uint32_t* d_out_mont, uint32_t* d_out_canon, cudaStream_t s,
-                uint32_t* d_out_xyzz = nullptr) {
+                uint32_t* d_out_xyzz = nullptr, const MsmChunk* ck = nullptr) {
     if (n == 0 || batch == 0) {
         if (d_out_mont) CU(cudaMemsetAsync(d_out_mont, 0, 96 * (size_t)std::max(batch, 1u), s));
         if (d_out_canon) CU(cudaMemsetAsync(d_out_canon, 0, 96 * (size_t)std::max(batch, 1u), s));
         return B200ZK_OK;
     }
     if (n >= (1ull << 31)) return fail(B200ZK_ERR_INVALID_ARG, "msm: n must be < 2^31");
-    MsmPlan pl = msm_plan(n, batch, tab);
+    MsmPlan pl = msm_plan(ck ? ck->n_total : n, batch, tab);
     uint64_t nwin = (uint64_t)batch * (pl.precomp ? 1 : pl.W);   // bucket sets
     uint64_t NBt = nwin * pl.nb;
     uint64_t max_entries = (uint64_t)batch * n * pl.W;
@@ -261,6 +271,7 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     TRY(g.heavy.ensure((4 + 3 * hmax + 2 * imax) * 4));
     TRY(g.heavy_items.ensure(imax * 192));
     TRY(g.buckets.ensure(NBt * 192));
+    if (ck && !ck->first) TRY(g.buckets2.ensure(NBt * 192));
     TRY(g.partials.ensure(max_tasks * 192));
     uint64_t m1 = (pl.nb + RED_RADIX - 1) / RED_RADIX, m2 = (m1 + RED_RADIX - 1) / RED_RADIX;
     TRY(g.redS[0].ensure(nwin * m1 * 192));
@@ -274,7 +285,8 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     uint32_t* ntask = g.ntask.as<uint32_t>();
     uint32_t* task_off = g.task_off.as<uint32_t>();
     uint32_t* entries = g.entries.as<uint32_t>();
-    uint32_t* buckets = g.buckets.as<uint32_t>();
+    uint32_t* buckets = (ck && !ck->first) ? g.buckets2.as<uint32_t>() : g.buckets.as<uint32_t>();
+    const uint64_t i0 = ck ? ck->i0 : 0;
     uint32_t* partials = g.partials.as<uint32_t>();
 
     TRY(ws_enter(s));
@@ -286,7 +298,7 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     const uint32_t fmt_mont = scalar_fmt == B200ZK_FMT_MONT ? 1u : 0u;
     // (A two-pass sort -- coarse bins of 2048 buckets staged through shared memory, then one CTA per bin --
     // was built and measured at 2^24: 11.0 ms against 7.9 ms for this one-pass histogram + scatter; removed.)
-    LAUNCH(msm_digits_kernel<0>, dgrid, 256, 0, s, d_scalars, n, fmt_mont, pl, counts, (uint32_t*)nullptr, 0u, 0xffffffffu, (const uint32_t*)nullptr, 0u);
+    LAUNCH(msm_digits_kernel<0>, dgrid, 256, 0, s, d_scalars, n, fmt_mont, pl, counts, (uint32_t*)nullptr, 0u, 0xffffffffu, (const uint32_t*)nullptr, 0u, i0);
     TRY(scan_u32(counts, offsets, NBt + 1, 0, s));
     CU(cudaMemcpyAsync(cursor, offsets, (NBt + 1) * 4, cudaMemcpyDeviceToDevice, s));
     {
@@ -302,7 +314,7 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
         for (uint32_t ps = 0; ps < passes; ps++) {
             uint32_t lo = (uint32_t)(NBt * ps / passes), hi = (uint32_t)(NBt * (ps + 1) / passes);
             LAUNCH(msm_digits_kernel<1>, dgrid, 256, 0, s, d_scalars, n, fmt_mont, pl, cursor, entries, lo, hi,
-                   passes > 1 ? (const uint32_t*)(offsets + NBt) : (const uint32_t*)nullptr, 100u << 20);
+                   passes > 1 ? (const uint32_t*)(offsets + NBt) : (const uint32_t*)nullptr, 100u << 20, i0);
         }
     }
     unsigned bgrid = (unsigned)((NBt + 255) / 256);
@@ -359,6 +371,15 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     TRY(prof_mark(2, s));
     LAUNCH(msm_collapse_kernel, (unsigned)(g.prop.multiProcessorCount * 4), 128, 0, s, (const uint32_t*)ntask,
            (const uint32_t*)task_off, hv, (const uint32_t*)partials, g.heavy_items.as<uint32_t>(), buckets);
+
+    if (ck && !ck->first)
+        LAUNCH(msm_bucket_merge_kernel, (unsigned)((NBt + 127) / 128), 128, 0, s, g.buckets.as<uint32_t>(), (const uint32_t*)buckets, NBt);
+    if (ck && !ck->last) {
+        TRY(ws_leave(s));
+        g.last_plan = pl;
+        return B200ZK_OK;
+    }
+    buckets = g.buckets.as<uint32_t>();
 
     // bucket reduction tree: work-efficient serial radix-16 groups while there are enough of them to fill
     // the machine, then warp-cooperative radix-32 groups (short dependency chains) for the upper levels
@@ -856,10 +877,16 @@ int32_t b200zk_shutdown(void) {
     g.coset_tables.clear();
     if (g.fixed_table) { cudaFree(g.fixed_table); g.fixed_table = nullptr; }
     DevBuf* all[] = {&g.scalars, &g.counts, &g.offsets, &g.cursor, &g.ntask, &g.task_off, &g.entries, &g.task_bucket,
-                     &g.task_start, &g.task_len, &g.buckets, &g.partials, &g.len_hist, &g.len_off, &g.order, &g.heavy, &g.heavy_items, &g.adhoc, &g.aff_a, &g.aff_b, &g.aff_pre, &g.redS[0], &g.redS[1], &g.redA[0], &g.redA[1],
+                     &g.task_start, &g.task_len, &g.buckets, &g.partials, &g.len_hist, &g.len_off, &g.order, &g.heavy, &g.heavy_items, &g.adhoc, &g.buckets2, &g.aff_a, &g.aff_b, &g.aff_pre, &g.redS[0], &g.redS[1], &g.redA[0], &g.redA[1],
                      &g.scan_tmp[0], &g.scan_tmp[1], &g.out_mont, &g.out_canon, &g.stage, &g.flag, &g.ntt_data,
                      &g.ntt_tmp[0], &g.ntt_tmp[1], &g.small};
     for (DevBuf* b : all) b->release();
+    if (g.copy_stream) {
+        cudaStreamDestroy(g.copy_stream);
+        cudaEventDestroy(g.copy_ev[0]);
+        cudaEventDestroy(g.copy_ev[1]);
+        g.copy_stream = nullptr;
+    }
     if (g.ws_event) { cudaEventDestroy(g.ws_event); g.ws_event = nullptr; }
     g.ws_used = false;
     if (g.stream) cudaStreamDestroy(g.stream);
@@ -993,8 +1020,34 @@ int32_t b200zk_msm_g1_batch(uint64_t bases, uint64_t offset, const uint8_t* scal
     size_t bytes = (size_t)n * batch * 32;
     TRY(g.scalars.ensure(bytes + 16));
     TRY(g.out_canon.ensure((size_t)batch * 96));
-    if (bytes) CU(cudaMemcpyAsync(g.scalars.p, scalars, bytes, cudaMemcpyHostToDevice, g.stream));
-    TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>(), n, batch, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream));
+    static int64_t chunk_min = -1;   // a single MSM of at least this many points streams its scalars in two pieces
+    if (chunk_min < 0) { const char* v = getenv("B200ZK_MSM_CHUNK_MIN"); chunk_min = v ? atoll(v) : (1ll << 23); }
+    if (batch == 1 && chunk_min > 0 && n >= (uint64_t)chunk_min) {
+        // The second piece of the scalars crosses PCIe while the first is sorted and accumulated: the first piece's
+        // buckets are g.buckets, the second accumulates into g.buckets2 and is folded in before the tail.
+        if (!g.copy_stream) {
+            CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&g.copy_ev[0], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&g.copy_ev[1], cudaEventDisableTiming));
+        }
+        // first piece = 1/8 of the points: its copy (1.2 ms at 2^24) is the only exposed transfer, and its sort + accumulate
+        // (9 ms) cover the copy of the other 7/8 (8.5 ms).  Measured at 2^24: 84.9 ms unchunked, 83.1 ms with halves.
+        const uint64_t nA = (n / 8 + 255) & ~(uint64_t)255, nB = n - nA;
+        uint8_t* d_sc = g.scalars.as<uint8_t>();
+        CU(cudaMemcpyAsync(d_sc, scalars, nA * 32, cudaMemcpyHostToDevice, g.copy_stream));
+        CU(cudaEventRecord(g.copy_ev[0], g.copy_stream));
+        CU(cudaMemcpyAsync(d_sc + nA * 32, scalars + nA * 32, nB * 32, cudaMemcpyHostToDevice, g.copy_stream));
+        CU(cudaEventRecord(g.copy_ev[1], g.copy_stream));
+        MsmChunk ca{n, 0, true, false}, cb{n, nA, false, true};
+        CU(cudaStreamWaitEvent(g.stream, g.copy_ev[0], 0));
+        TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>(), nA, 1, scalar_fmt, nullptr, nullptr, g.stream, nullptr, &ca));
+        CU(cudaStreamWaitEvent(g.stream, g.copy_ev[1], 0));
+        TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>() + 8 * nA, nB, 1, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream,
+                    nullptr, &cb));
+    } else {
+        if (bytes) CU(cudaMemcpyAsync(g.scalars.p, scalars, bytes, cudaMemcpyHostToDevice, g.stream));
+        TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>(), n, batch, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream));
+    }
     CU(cudaMemcpyAsync(out_affine, g.out_canon.p, (size_t)batch * 96, cudaMemcpyDeviceToHost, g.stream));
     CU(cudaStreamSynchronize(g.stream));
     return B200ZK_OK;

@@ -70,7 +70,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const uint32_t* __restrict__ scalars, uint64_t n, uint32_t fmt_mont,
                                                          MsmPlan pl, uint32_t* __restrict__ counts_or_cursor,
                                                          uint32_t* __restrict__ entries, uint32_t g_lo, uint32_t g_hi,
-                                                         const uint32_t* __restrict__ total_entries, uint32_t split_min) {
+                                                         const uint32_t* __restrict__ total_entries, uint32_t split_min,
+                                                         uint64_t i0) {
     // Range passes only pay when the entry array is far larger than L2 (uniform scalars); with few entries (skewed
     // prover columns) the first pass takes the whole range and the others leave at once.  The count is on the device.
     if (MODE == 1 && total_entries) {
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint32_t* __restr
         if (MODE == 1) {
             pos = __shfl_sync(0xffffffffu, pos, leader);
             if (valid) {
-                uint32_t idx = pl.precomp ? (uint32_t)(w * pl.row_stride + i) : (uint32_t)i;
+                uint32_t idx = pl.precomp ? (uint32_t)(w * pl.row_stride + i0 + i) : (uint32_t)(i0 + i);   // i0: first point of this chunk
                 entries[pos + rank] = idx | (d < 0 ? 0x80000000u : 0u);
             }
         }
@@ -383,6 +384,19 @@ __global__ void __launch_bounds__(128) msm_collapse_kernel(const uint32_t* __res
             if (lane == 0) xyzz_st(buckets, g, tot);
         }
     }
+}
+
+// buckets[g] += other[g]: folds the bucket set of a later scalar chunk (host-buffer MSMs stream their scalars in two
+// halves so that the second H2D copy runs under the first half's accumulation) into the first one
+__global__ void __launch_bounds__(128) msm_bucket_merge_kernel(uint32_t* __restrict__ buckets, const uint32_t* __restrict__ other,
+                                                               uint64_t nbuckets) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nbuckets) return;
+    G1Xyzz b = xyzz_ld(other, g);
+    if (xyzz_is_inf(b)) return;
+    G1Xyzz a = xyzz_ld(buckets, g);
+    xyzz_add_ni(a, b);
+    xyzz_st(buckets, g, a);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -397,3 +397,37 @@ def test_calls_on_different_streams_do_not_race(gpu, oracle):
         for i in range(4):
             assert bytes(d_out[i].cpu().numpy()) == want[i], (rep, i)
     chk(lib.b200zk_bases_release(h.value))
+
+
+def test_chunked_host_buffer_path_small_sizes(gpu):
+    """A host-buffer MSM of >= B200ZK_MSM_CHUNK_MIN points streams its scalars in two halves (second bucket set, merge
+    kernel).  The default threshold is 2^22; a child process lowers it to 512 so that ragged small sizes, skewed scalars
+    and tables with and without window rows go through that path against the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import ctypes as C, importlib, os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+from conftest import Oracle, _build_oracle
+zk = importlib.import_module("plutus-halo2-verifier-gen_b200")
+zk.init(-1)
+orc = Oracle(_build_oracle())
+lib, chk, addr = zk.lib(), zk.capi.check, zk.capi.addr
+R = zk.host.R_MOD
+for n, flags in ((512, 0), (777, 0), (4099, 0), (4099, 0x100), (20000, 0)):
+    bases = orc.synth_bases(0xB200, 5, n)
+    h = C.c_uint64(0)
+    chk(lib.b200zk_bases_register(addr(bases), n, zk.FMT_CANONICAL | flags, 96, C.byref(h)))
+    for sc in (orc.synth_scalars(70 + n, 0, n), (R - 1).to_bytes(32, "little") * n,
+               b"".join((i %% 2).to_bytes(32, "little") for i in range(n))):
+        out = C.create_string_buffer(96)
+        chk(lib.b200zk_msm_g1(h.value, 0, addr(sc), n, zk.FMT_CANONICAL, addr(out)))
+        assert out.raw == orc.msm(bases, sc, n), (n, flags)
+    chk(lib.b200zk_bases_release(h.value))
+print("chunked ok")
+''' % (root, root)
+    env = dict(os.environ, B200ZK_MSM_CHUNK_MIN="512")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "chunked ok" in r.stdout, r.stdout + r.stderr
