@@ -1044,6 +1044,26 @@ int32_t b200zk_msm_g1_batch(uint64_t bases, uint64_t offset, const uint8_t* scal
         CU(cudaStreamWaitEvent(g.stream, g.copy_ev[1], 0));
         TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>() + 8 * nA, nB, 1, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream,
                     nullptr, &cb));
+    } else if (batch >= 4 && chunk_min > 0 && bytes >= (64ull << 20)) {
+        // The prover's pattern (all columns of a phase in one call): the columns are independent, so the first eighth of
+        // them goes up and starts computing while the others cross PCIe; no merge is needed.
+        if (!g.copy_stream) {
+            CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&g.copy_ev[0], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&g.copy_ev[1], cudaEventDisableTiming));
+        }
+        const uint32_t bA = std::max(1u, batch / 8), bB = batch - bA;
+        const size_t col = (size_t)n * 32;
+        uint8_t* d_sc = g.scalars.as<uint8_t>();
+        CU(cudaMemcpyAsync(d_sc, scalars, bA * col, cudaMemcpyHostToDevice, g.copy_stream));
+        CU(cudaEventRecord(g.copy_ev[0], g.copy_stream));
+        CU(cudaMemcpyAsync(d_sc + bA * col, scalars + bA * col, bB * col, cudaMemcpyHostToDevice, g.copy_stream));
+        CU(cudaEventRecord(g.copy_ev[1], g.copy_stream));
+        CU(cudaStreamWaitEvent(g.stream, g.copy_ev[0], 0));
+        TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>(), n, bA, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream));
+        CU(cudaStreamWaitEvent(g.stream, g.copy_ev[1], 0));
+        TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>() + 8 * (size_t)n * bA, n, bB, scalar_fmt, nullptr,
+                    g.out_canon.as<uint32_t>() + 24 * (size_t)bA, g.stream));
     } else {
         if (bytes) CU(cudaMemcpyAsync(g.scalars.p, scalars, bytes, cudaMemcpyHostToDevice, g.stream));
         TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>(), n, batch, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream));

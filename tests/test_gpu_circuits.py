@@ -114,3 +114,17 @@ def test_kzg_coefficient_and_lagrange_commitments_agree(gpu, oracle, pyref):
     left, right = dual.eval()
     assert oracle.g1_mul(left, fr(s)) == right
     params.release()
+
+
+def test_streamed_column_batch(gpu, oracle):
+    """A batched commitment of >= 64 MiB of scalars (atms k=17: 16 columns) goes up in two groups of columns, the second
+    copy running under the first group's MSMs: every column on both sides of the split must match the oracle."""
+    k, batch = 17, 16
+    n = 1 << k
+    g = oracle.synth_bases(0xB200, 0, n)
+    params = gpu.host.ParamsKZG(k, g)
+    cols = [oracle.synth_scalars(600 + i, 0, n) if i % 3 else prover_like_column(oracle, 600 + i, n) for i in range(batch)]
+    got = gpu.host.KZGCommitmentScheme.commit_batch(params, cols)
+    for i in (0, 1, 2, 3, 8, 15):
+        assert got[i] == oracle.msm(g, cols[i], n), i
+    params.release()
