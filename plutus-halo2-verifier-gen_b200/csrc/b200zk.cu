@@ -1022,6 +1022,10 @@ int32_t b200zk_msm_g1_batch(uint64_t bases, uint64_t offset, const uint8_t* scal
     TRY(g.out_canon.ensure((size_t)batch * 96));
     static int64_t chunk_min = -1;   // a single MSM of at least this many points streams its scalars in two pieces
     if (chunk_min < 0) { const char* v = getenv("B200ZK_MSM_CHUNK_MIN"); chunk_min = v ? atoll(v) : (1ll << 23); }
+    // batches of columns: worth two passes only when the transfer is long (measured: 75 MB at k = 17 loses 0.7 ms, 288 MB at
+    // k = 19 gains 3.3 ms)
+    static size_t batch_stream_min = 0;
+    if (!batch_stream_min) { const char* v = getenv("B200ZK_BATCH_STREAM_MIN_BYTES"); batch_stream_min = v ? (size_t)atoll(v) : ((size_t)128 << 20); if (!batch_stream_min) batch_stream_min = 1; }
     if (batch == 1 && chunk_min > 0 && n >= (uint64_t)chunk_min) {
         // The second piece of the scalars crosses PCIe while the first is sorted and accumulated: the first piece's
         // buckets are g.buckets, the second accumulates into g.buckets2 and is folded in before the tail.
@@ -1044,7 +1048,7 @@ int32_t b200zk_msm_g1_batch(uint64_t bases, uint64_t offset, const uint8_t* scal
         CU(cudaStreamWaitEvent(g.stream, g.copy_ev[1], 0));
         TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>() + 8 * nA, nB, 1, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream,
                     nullptr, &cb));
-    } else if (batch >= 4 && chunk_min > 0 && bytes >= (64ull << 20)) {
+    } else if (batch >= 4 && chunk_min > 0 && bytes >= batch_stream_min) {
         // The prover's pattern (all columns of a phase in one call): the columns are independent, so the first eighth of
         // them goes up and starts computing while the others cross PCIe; no merge is needed.
         if (!g.copy_stream) {

@@ -116,15 +116,32 @@ def test_kzg_coefficient_and_lagrange_commitments_agree(gpu, oracle, pyref):
     params.release()
 
 
-def test_streamed_column_batch(gpu, oracle):
-    """A batched commitment of >= 64 MiB of scalars (atms k=17: 16 columns) goes up in two groups of columns, the second
-    copy running under the first group's MSMs: every column on both sides of the split must match the oracle."""
-    k, batch = 17, 16
+def test_streamed_column_batch(gpu):
+    """A batched commitment with a long transfer (>= 128 MiB of scalars, e.g. 18 columns at k = 19) goes up in two groups of
+    columns, the second copy running under the first group's MSMs.  A child process lowers the threshold so that a small
+    batch takes that path: every column on both sides of the split must match the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import ctypes as C, importlib, os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+from conftest import Oracle, _build_oracle
+zk = importlib.import_module("plutus-halo2-verifier-gen_b200")
+zk.init(-1)
+orc = Oracle(_build_oracle())
+for k, batch in ((10, 4), (12, 9), (13, 16)):
     n = 1 << k
-    g = oracle.synth_bases(0xB200, 0, n)
-    params = gpu.host.ParamsKZG(k, g)
-    cols = [oracle.synth_scalars(600 + i, 0, n) if i % 3 else prover_like_column(oracle, 600 + i, n) for i in range(batch)]
-    got = gpu.host.KZGCommitmentScheme.commit_batch(params, cols)
-    for i in (0, 1, 2, 3, 8, 15):
-        assert got[i] == oracle.msm(g, cols[i], n), i
+    g = orc.synth_bases(0xB200, 0, n)
+    params = zk.host.ParamsKZG(k, g)
+    cols = [orc.synth_scalars(600 + i, 0, n) for i in range(batch)]
+    got = zk.host.KZGCommitmentScheme.commit_batch(params, cols)
+    for i in range(batch):
+        assert got[i] == orc.msm(g, cols[i], n), (k, i)
     params.release()
+print("streamed ok")
+''' % (root, root)
+    env = dict(os.environ, B200ZK_BATCH_STREAM_MIN_BYTES="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "streamed ok" in r.stdout, r.stdout + r.stderr
