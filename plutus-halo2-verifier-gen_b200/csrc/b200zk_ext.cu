@@ -46,7 +46,7 @@ struct GateProgram {
 struct Ext {
     bool hooked = false;
     Buf scratch, totals, stage, small, colptr, omega_pows, status;
-    size_t small_off = 0;
+    size_t small_off = 0, colptr_off = 0;
     uint32_t* fixed_table = nullptr;   // 32 x 256 multiples of G
     std::map<uint64_t, GateProgram> programs;
     uint64_t next_program = 1;
@@ -65,6 +65,7 @@ void ext_shutdown() {
     }
     x.programs.clear();
     x.small_off = 0;
+    x.colptr_off = 0;
 }
 
 int32_t enter() {
@@ -518,7 +519,7 @@ int32_t b200zk_gate_program_run_dev(uint64_t handle, const void* const* d_column
     cudaStream_t s = S(stream);
     // column pointers ride in a small ring like the host scalars (stream-ordered copy)
     XTRY(x.colptr.ensure(SMALL_BYTES));
-    static size_t off = 0;
+    size_t& off = x.colptr_off;
     size_t bytes = ((size_t)gp.n_columns * 8 + 63) & ~(size_t)63;
     if (bytes > SMALL_BYTES / 2) return ctx::fail(B200ZK_ERR_INVALID_ARG, "gate program: too many columns");
     if (off + bytes > SMALL_BYTES) off = 0;

@@ -8,15 +8,22 @@
 // /root/reference/aiken-verifier/aiken_halo2/lib/halo2_kzg.ak:15-44).
 //
 // Pipeline (all on the device, one stream):
-//   1. digits    : 255-bit scalars -> W signed c-bit digits; histogram of (window, |digit|) buckets
+//   1. digits    : 255-bit scalars -> W signed c-bit digits; histogram of (row, |digit|) buckets
 //   2. scan      : bucket offsets
-//   3. scatter   : point index (+ sign bit) written to its bucket's slice  (counting sort)
+//   3. scatter   : point index (+ sign bit) written to its bucket's slice (counting sort); for bucket sets whose open
+//                  32-byte sectors do not fit in L2 it runs as two bucket-range passes (decided on the device)
 //   4. tasks     : every bucket becomes ceil(count / smax) tasks of <= smax entries, so a heavy
-//                  bucket (skewed prover scalars: 0/1 columns) cannot serialise the kernel
-//   5. accumulate: one thread per task, XYZZ accumulator += affine base (8M+2S per point)
+//                  bucket (skewed prover scalars: 0/1 columns) cannot serialise the kernel; tasks are ordered by length
+//   5. accumulate: one thread per task, XYZZ accumulator += affine base: 6 products, 2 dedicated squarings and one fused
+//                  product pair per point (field.cuh)
 //   6. collapse  : buckets that were split are summed from their task partials (one warp each)
-//   7. reduce    : sum_b b*B_b per window by a radix-16 running-sum tree
-//   8. combine   : Horner over the windows, affine normalisation, wire-format output
+//   7. reduce    : sum_b b*B_b by a running-sum tree: serial radix-16 groups while there are >= 4096 of them, then
+//                  warp-cooperative radix-32 groups, the last levels with 8 lanes per node
+//   8. combine   : Horner over the windows (none with window tables; warp-cooperative doublings otherwise), affine
+//                  normalisation, wire-format output
+// With window tables (rows 2^(c*w) * P_i built at registration) all windows share ONE bucket set.  Host-buffer MSMs of
+// >= 2^23 points stream their scalars in two pieces; the second piece accumulates into a second bucket set that
+// msm_bucket_merge_kernel folds in before step 7.
 #pragma once
 #include "affine_tree.cuh"
 #include "g1.cuh"
