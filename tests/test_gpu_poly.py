@@ -220,3 +220,27 @@ def test_compiled_gates_on_device(gpu, pyref):
             want = (want * challenges[0] + _eval_expr(scaled(g), cols, row, n_ext, challenges)) % R
         assert out[row] == want, row
     gp.release()
+
+
+def test_extend_and_power_table(gpu, pyref):
+    """b200zk_fr_extend_dev (zero padding of coeff_to_extended on the device, batched) and b200zk_fr_power_table_dev
+    (the omega^(i2 k1) block of the multi-GPU transform) against their definitions."""
+    import ctypes as C
+    H = gpu.host
+    lib, chk = gpu.lib(), gpu.capi.check
+    rng = random.Random(5)
+    n_in, n_out, batch = 24, 64, 3
+    vals = rand_fr(rng, n_in * batch)
+    src = H.FrVec.from_ints(vals)
+    dst = H.FrVec(n_out * batch)
+    chk(lib.b200zk_fr_extend_dev(src.ptr, n_in, dst.ptr, n_out, batch, None))
+    got = dst.to_ints()
+    for b in range(batch):
+        assert got[b * n_out:b * n_out + n_in] == vals[b * n_in:(b + 1) * n_in]
+        assert got[b * n_out + n_in:(b + 1) * n_out] == [0] * (n_out - n_in)
+    base = rng.randrange(R)
+    row0, rows, cols = 5, 7, 9
+    tab = H.FrVec(rows * cols)
+    bb = base.to_bytes(32, "little")
+    chk(lib.b200zk_fr_power_table_dev(gpu.capi.addr(bb), row0, rows, cols, tab.ptr, None))
+    assert tab.to_ints() == [pow(base, (row0 + r) * c, R) for r in range(rows) for c in range(cols)]

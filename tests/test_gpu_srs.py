@@ -127,3 +127,16 @@ def test_batched_verifier_front_end(gpu, oracle):
         msm.append_right(int.from_bytes(sc[32 * i:32 * i + 32], "little"), aff[96 * i:96 * i + 96])
     _, right = msm.eval()
     assert right == oracle.msm(pts, sc, n)
+
+
+def test_fixed_base_mul_montgomery_scalars(gpu, oracle):
+    """the same scalars in Montgomery form (the in-memory form of midnight_curves::Fq) give the same points"""
+    H = gpu.host
+    vals = [3, R - 5, 0x1234567890ABCDEF << 100]
+    sc = H.FrVec.from_ints(vals)                       # Montgomery form on the device
+    out = H.DeviceBuffer(96 * len(vals))
+    gpu.capi.check(gpu.lib().b200zk_g1_fixed_mul_dev(sc.ptr, gpu.FMT_MONT, len(vals), out.ptr, None))
+    got = H.g1_export(out, len(vals))
+    G = oracle.g1_generator()
+    for i, v in enumerate(vals):
+        assert got[96 * i:96 * i + 96] == oracle.g1_mul(G, fr(v)), hex(v)
