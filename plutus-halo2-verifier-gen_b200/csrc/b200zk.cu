@@ -1036,15 +1036,22 @@ int32_t b200zk_msm_g1_batch(uint64_t bases, uint64_t offset, const uint8_t* scal
         }
         // first piece = 1/8 of the points: its copy (1.2 ms at 2^24) is the only exposed transfer, and its sort + accumulate
         // (9 ms) cover the copy of the other 7/8 (8.5 ms).  Measured at 2^24: 84.9 ms unchunked, 83.1 ms with halves.
-        const uint64_t nA = (n / 8 + 255) & ~(uint64_t)255, nB = n - nA;
+        // From pageable memory (a plain Rust Vec) the copy runs at ~11 GB/s instead of ~55: the balance point
+        // copy(rest) = compute(first) moves from 1/8 to 3/8 (measured at 2^24, pageable: 122.8 ms unchunked, 118.7 with 1/8).
+        cudaPointerAttributes pa{};
+        bool pinned = cudaPointerGetAttributes(&pa, scalars) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const uint64_t nA = ((pinned ? n / 8 : 3 * (n / 8)) + 255) & ~(uint64_t)255, nB = n - nA;
         uint8_t* d_sc = g.scalars.as<uint8_t>();
+        // (the first piece's kernels are enqueued before the second copy is issued: from pageable host memory a copy
+        // blocks the calling thread, and the device must already have work by then)
+        MsmChunk ca{n, 0, true, false}, cb{n, nA, false, true};
         CU(cudaMemcpyAsync(d_sc, scalars, nA * 32, cudaMemcpyHostToDevice, g.copy_stream));
         CU(cudaEventRecord(g.copy_ev[0], g.copy_stream));
-        CU(cudaMemcpyAsync(d_sc + nA * 32, scalars + nA * 32, nB * 32, cudaMemcpyHostToDevice, g.copy_stream));
-        CU(cudaEventRecord(g.copy_ev[1], g.copy_stream));
-        MsmChunk ca{n, 0, true, false}, cb{n, nA, false, true};
         CU(cudaStreamWaitEvent(g.stream, g.copy_ev[0], 0));
         TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>(), nA, 1, scalar_fmt, nullptr, nullptr, g.stream, nullptr, &ca));
+        CU(cudaMemcpyAsync(d_sc + nA * 32, scalars + nA * 32, nB * 32, cudaMemcpyHostToDevice, g.copy_stream));
+        CU(cudaEventRecord(g.copy_ev[1], g.copy_stream));
         CU(cudaStreamWaitEvent(g.stream, g.copy_ev[1], 0));
         TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>() + 8 * nA, nB, 1, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream,
                     nullptr, &cb));
@@ -1061,10 +1068,10 @@ int32_t b200zk_msm_g1_batch(uint64_t bases, uint64_t offset, const uint8_t* scal
         uint8_t* d_sc = g.scalars.as<uint8_t>();
         CU(cudaMemcpyAsync(d_sc, scalars, bA * col, cudaMemcpyHostToDevice, g.copy_stream));
         CU(cudaEventRecord(g.copy_ev[0], g.copy_stream));
-        CU(cudaMemcpyAsync(d_sc + bA * col, scalars + bA * col, bB * col, cudaMemcpyHostToDevice, g.copy_stream));
-        CU(cudaEventRecord(g.copy_ev[1], g.copy_stream));
         CU(cudaStreamWaitEvent(g.stream, g.copy_ev[0], 0));
         TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>(), n, bA, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream));
+        CU(cudaMemcpyAsync(d_sc + bA * col, scalars + bA * col, bB * col, cudaMemcpyHostToDevice, g.copy_stream));
+        CU(cudaEventRecord(g.copy_ev[1], g.copy_stream));
         CU(cudaStreamWaitEvent(g.stream, g.copy_ev[1], 0));
         TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>() + 8 * (size_t)n * bA, n, bB, scalar_fmt, nullptr,
                     g.out_canon.as<uint32_t>() + 24 * (size_t)bA, g.stream));
