@@ -665,6 +665,77 @@ void orc_ntt(uint8_t *data, uint32_t log_n, const uint8_t omega[32], uint32_t fl
     free(a);
 }
 
+/* ------------------------------------------------------------------ polynomial side
+ * Plain serial restatements, the checker for the Fr vector kernels at sizes the big-int oracle cannot walk.
+ * All vectors are canonical 32-byte little-endian elements. */
+static int fr_is_zero_(const fr *a) { return (a->l[0] | a->l[1] | a->l[2] | a->l[3]) == 0; }
+
+/* synthetic division by (X - z): quot[i-1] = s_i, eval = s_0, s_i = c_i + z s_{i+1}  (the witness polynomials of the
+ * KZG multi-open, /root/reference/src/plutus_gen/extraction/pcs/kzg.rs:55-79) */
+void orc_fr_kate_div(const uint8_t *coeffs, u64 n, const uint8_t z[32], uint8_t *quot, uint8_t eval[32]) {
+    orc_init();
+    fr zz, s, c;
+    fr_from_bytes(&zz, z);
+    memset(&s, 0, sizeof(s));
+    for (u64 k = n; k-- > 0;) {
+        fr_from_bytes(&c, coeffs + 32 * k);
+        fr_mul(&s, &s, &zz);
+        fr_add(&s, &s, &c);
+        if (k && quot) fr_to_bytes(quot + 32 * (k - 1), &s);
+    }
+    if (eval) fr_to_bytes(eval, &s);
+}
+/* out[i] = init * prod_{j<i} in[j] (exclusive) or prod_{j<=i} (inclusive): the grand products of the permutation /
+ * lookup arguments (/root/reference/src/plutus_gen/extraction/data/extraction_steps/permutation.rs) */
+void orc_fr_running_product(const uint8_t *in, u64 n, const uint8_t *init, int inclusive, uint8_t *out) {
+    orc_init();
+    fr acc, v, nxt;
+    if (init) fr_from_bytes(&acc, init);
+    else memcpy(acc.l, FR_R, 32);
+    for (u64 i = 0; i < n; i++) {
+        fr_from_bytes(&v, in + 32 * i);
+        fr_mul(&nxt, &acc, &v);
+        fr_to_bytes(out + 32 * i, inclusive ? &nxt : &acc);
+        acc = nxt;
+    }
+}
+/* elementwise inverse, zeros stay zero (halo2 batch_invert); Montgomery's trick over the whole vector */
+void orc_fr_batch_invert(const uint8_t *in, u64 n, uint8_t *out) {
+    orc_init();
+    fr *pre = (fr *)malloc(sizeof(fr) * (n ? n : 1)), run, v, inv;
+    memcpy(run.l, FR_R, 32);
+    for (u64 i = 0; i < n; i++) {
+        pre[i] = run;
+        fr_from_bytes(&v, in + 32 * i);
+        if (!fr_is_zero_(&v)) fr_mul(&run, &run, &v);
+    }
+    fr_inv(&inv, &run);
+    for (u64 i = n; i-- > 0;) {
+        fr_from_bytes(&v, in + 32 * i);
+        if (fr_is_zero_(&v)) { memset(out + 32 * i, 0, 32); continue; }
+        fr r;
+        fr_mul(&r, &inv, &pre[i]);
+        fr_to_bytes(out + 32 * i, &r);
+        fr_mul(&inv, &inv, &v);
+    }
+    free(pre);
+}
+/* out = sum_k coeffs[k] * polys[k] (polys stored back to back, n elements each) */
+void orc_fr_lincomb(const uint8_t *polys, const uint8_t *coeffs, u64 count, u64 n, uint8_t *out) {
+    orc_init();
+    for (u64 i = 0; i < n; i++) {
+        fr acc, c, v;
+        memset(&acc, 0, sizeof(acc));
+        for (u64 k = 0; k < count; k++) {
+            fr_from_bytes(&c, coeffs + 32 * k);
+            fr_from_bytes(&v, polys + 32 * (k * n + i));
+            fr_mul(&v, &v, &c);
+            fr_add(&acc, &acc, &v);
+        }
+        fr_to_bytes(out + 32 * i, &acc);
+    }
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -42,6 +42,10 @@ class Oracle:
         L.orc_fr_dot_u64.argtypes = [C.c_char_p, C.c_void_p, u64, C.c_char_p]
         L.orc_ntt.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_char_p, C.c_char_p, C.c_int]
         L.orc_ntt_naive.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
+        L.orc_fr_kate_div.argtypes = [C.c_char_p, u64, C.c_char_p, C.c_char_p, C.c_char_p]
+        L.orc_fr_running_product.argtypes = [C.c_char_p, u64, C.c_char_p, C.c_int, C.c_char_p]
+        L.orc_fr_batch_invert.argtypes = [C.c_char_p, u64, C.c_char_p]
+        L.orc_fr_lincomb.argtypes = [C.c_char_p, C.c_char_p, u64, u64, C.c_char_p]
 
     def msm(self, points: bytes, scalars: bytes, n: int, naive=False) -> bytes:
         out = C.create_string_buffer(96)
@@ -95,6 +99,29 @@ class Oracle:
         buf = C.create_string_buffer(data, len(data))
         self.L.orc_ntt_naive(buf, log_n, omega)
         return buf.raw
+
+    def kate_div(self, coeffs: bytes, z: bytes):
+        n = len(coeffs) // 32
+        quot = C.create_string_buffer(32 * max(n - 1, 1))
+        ev = C.create_string_buffer(32)
+        self.L.orc_fr_kate_div(coeffs, n, z, quot, ev)
+        return quot.raw[:32 * max(n - 1, 0)], ev.raw
+
+    def running_product(self, v: bytes, init: bytes = None, inclusive=False) -> bytes:
+        out = C.create_string_buffer(max(len(v), 1))
+        self.L.orc_fr_running_product(v, len(v) // 32, init, 1 if inclusive else 0, out)
+        return out.raw[:len(v)]
+
+    def batch_invert(self, v: bytes) -> bytes:
+        out = C.create_string_buffer(max(len(v), 1))
+        self.L.orc_fr_batch_invert(v, len(v) // 32, out)
+        return out.raw[:len(v)]
+
+    def lincomb(self, polys: bytes, coeffs: bytes, count: int) -> bytes:
+        n = len(polys) // 32 // count
+        out = C.create_string_buffer(32 * max(n, 1))
+        self.L.orc_fr_lincomb(polys, coeffs, count, n, out)
+        return out.raw[:32 * n]
 
     def field(self, name, a: bytes, b: bytes = None) -> bytes:
         n = 48 if name.startswith("orc_fp") else 32

@@ -121,3 +121,25 @@ def test_compile_gates_matches_tree_evaluation(zk, pyref):
                 for v in vals:
                     want = (want * challenges[y] + v) % R
             assert got[row] == want, (row, y)
+
+
+def test_c_oracle_polynomial_side_matches_bigint_oracle(oracle, pyref):
+    """the C restatements used as the checker at 2^20 (oracle/b200zk_oracle.c) against the big-int ones"""
+    rng = random.Random(8)
+    tb = lambda v: b"".join(x.to_bytes(32, "little") for x in v)
+    ti = lambda b: [int.from_bytes(b[32 * i:32 * i + 32], "little") for i in range(len(b) // 32)]
+    for n in (1, 2, 33, 500):
+        v = [rng.randrange(R) for _ in range(n)]
+        z = rng.randrange(R)
+        q, e = oracle.kate_div(tb(v), z.to_bytes(32, "little"))
+        wq, we = pyref.kate_div(v, z)
+        assert ti(q) == wq and int.from_bytes(e, "little") == we
+        assert ti(oracle.running_product(tb(v))) == pyref.running_product(v)
+        init = rng.randrange(R)
+        assert ti(oracle.running_product(tb(v), init.to_bytes(32, "little"), True)) == pyref.running_product(v, init, True)
+        vz = list(v)
+        vz[0] = 0
+        assert ti(oracle.batch_invert(tb(vz))) == pyref.batch_invert(vz)
+    polys = [[rng.randrange(R) for _ in range(40)] for _ in range(5)]
+    cs = [rng.randrange(R) for _ in range(5)]
+    assert ti(oracle.lincomb(b"".join(tb(p) for p in polys), tb(cs), 5)) == pyref.lincomb(polys, cs)
