@@ -128,7 +128,8 @@ struct Ctx {
     // NTT workspace
     DevBuf ntt_data, ntt_tmp[2], small;
     // second stream + events for host-buffer MSMs that stream their scalars in two halves
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, down_stream = nullptr;
+    std::vector<cudaEvent_t> pipe_up, pipe_done;
     cudaEvent_t copy_ev[2] = {nullptr, nullptr};
     // cross-stream ordering of the shared workspaces
     cudaEvent_t ws_event = nullptr;
@@ -881,6 +882,11 @@ int32_t b200zk_shutdown(void) {
                      &g.scan_tmp[0], &g.scan_tmp[1], &g.out_mont, &g.out_canon, &g.stage, &g.flag, &g.ntt_data,
                      &g.ntt_tmp[0], &g.ntt_tmp[1], &g.small};
     for (DevBuf* b : all) b->release();
+    if (g.down_stream) { cudaStreamDestroy(g.down_stream); g.down_stream = nullptr; }
+    for (cudaEvent_t e : g.pipe_up) cudaEventDestroy(e);
+    for (cudaEvent_t e : g.pipe_done) cudaEventDestroy(e);
+    g.pipe_up.clear();
+    g.pipe_done.clear();
     if (g.copy_stream) {
         cudaStreamDestroy(g.copy_stream);
         cudaEventDestroy(g.copy_ev[0]);
@@ -1190,6 +1196,44 @@ int32_t b200zk_ntt_fr_batch(uint8_t* data, uint32_t batch, uint32_t log_n, const
     if (batch == 0) return B200ZK_OK;
     size_t bytes = ((size_t)batch << log_n) * 32;
     TRY(g.ntt_data.ensure(bytes));
+    static int64_t pipe_min = -1;   // batches with at least this many bytes are pipelined group by group
+    if (pipe_min < 0) { const char* v = getenv("B200ZK_NTT_PIPE_MIN_BYTES"); pipe_min = v ? atoll(v) : (32ll << 20); }
+    if (batch >= 4 && pipe_min > 0 && bytes >= (size_t)pipe_min) {
+        // A transform is PCIe-bound end to end (2^22: 2.4 ms up, 0.94 ms of kernels, 2.4 ms down), and the link is full
+        // duplex: group g+1 goes up and group g-1 comes down while group g is transformed.
+        if (!g.copy_stream) {
+            CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&g.copy_ev[0], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&g.copy_ev[1], cudaEventDisableTiming));
+        }
+        if (!g.down_stream) CU(cudaStreamCreateWithFlags(&g.down_stream, cudaStreamNonBlocking));
+        const uint32_t groups = std::min<uint32_t>(8, batch / 2);
+        const size_t poly = ((size_t)1 << log_n) * 32;
+        std::vector<cudaEvent_t>& up = g.pipe_up;
+        std::vector<cudaEvent_t>& done = g.pipe_done;
+        while (up.size() < groups) {
+            cudaEvent_t e1, e2;
+            CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            up.push_back(e1);
+            done.push_back(e2);
+        }
+        uint8_t* d = g.ntt_data.as<uint8_t>();
+        for (uint32_t k = 0; k < groups; k++) {
+            const uint32_t b0 = (uint32_t)((uint64_t)batch * k / groups), b1 = (uint32_t)((uint64_t)batch * (k + 1) / groups);
+            const size_t off = b0 * poly, len = (size_t)(b1 - b0) * poly;
+            CU(cudaMemcpyAsync(d + off, data + off, len, cudaMemcpyHostToDevice, g.copy_stream));
+            CU(cudaEventRecord(up[k], g.copy_stream));
+            CU(cudaStreamWaitEvent(g.stream, up[k], 0));
+            TRY(ntt_run(reinterpret_cast<uint32_t*>(d + off), b1 - b0, log_n, omega, flags, coset_shift, g.stream));
+            CU(cudaEventRecord(done[k], g.stream));
+            CU(cudaStreamWaitEvent(g.down_stream, done[k], 0));
+            CU(cudaMemcpyAsync(data + off, d + off, len, cudaMemcpyDeviceToHost, g.down_stream));
+        }
+        CU(cudaStreamSynchronize(g.down_stream));
+        CU(cudaStreamSynchronize(g.stream));
+        return B200ZK_OK;
+    }
     CU(cudaMemcpyAsync(g.ntt_data.p, data, bytes, cudaMemcpyHostToDevice, g.stream));
     TRY(ntt_run(g.ntt_data.as<uint32_t>(), batch, log_n, omega, flags, coset_shift, g.stream));
     CU(cudaMemcpyAsync(data, g.ntt_data.p, bytes, cudaMemcpyDeviceToHost, g.stream));

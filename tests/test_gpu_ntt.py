@@ -156,3 +156,19 @@ def test_four_step_plan_single_rank_matches_library(gpu, oracle, pyref, log_n):
     inv = zdist.ShardedNTT(log_n, pyref.fr_inv(w), 0, 1, inverse=True).run(out)
     torch.cuda.synchronize()
     assert bytes(inv.cpu().numpy()) == data
+
+
+def test_pipelined_host_batch(gpu, oracle, pyref):
+    """Host-buffer batches of >= 32 MiB are pipelined group by group (upload of the next group and download of the previous
+    one under the current group's kernels): 8 x 2^17 elements, every polynomial against the oracle, plus coset + inverse."""
+    log_n, batch = 17, 8
+    n = 1 << log_n
+    data = oracle.synth_scalars(77, 0, n * batch)
+    w = pyref.omega(log_n)
+    got = gpu_ntt(gpu, data, log_n, w, batch=batch)
+    for b in range(batch):
+        assert got[32 * n * b:32 * n * (b + 1)] == oracle.ntt(data[32 * n * b:32 * n * (b + 1)], log_n, fr(w)), b
+    cos = gpu_ntt(gpu, data, log_n, w, gpu.NTT_COSET_IN, 7, batch=batch)
+    back = gpu_ntt(gpu, cos, log_n, pyref.fr_inv(w), gpu.NTT_INVERSE_SCALE | gpu.NTT_COSET_OUT, pyref.fr_inv(7), batch=batch)
+    assert back == data
+    assert cos[:32 * n] == oracle.ntt(data[:32 * n], log_n, fr(w), 0, fr(7))
