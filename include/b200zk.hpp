@@ -42,6 +42,22 @@ public:
         check(b200zk_bases_register(g, n_, fmt, stride, &g_));
         if (g_lagrange) check(b200zk_bases_register(g_lagrange, n_, fmt, stride, &gl_));
     }
+    // ParamsKZG::unsafe_setup (/root/reference/src/kzg_params.rs:43): both tables generated on the device for the secret s
+    // (canonical Fr) and the domain generator omega of order 2^k, and registered without leaving HBM.
+    static ParamsKZG unsafe_setup(uint32_t k, const std::array<uint8_t, 32>& s, const std::array<uint8_t, 32>& omega) {
+        ParamsKZG p(k);
+        void *g = nullptr, *gl = nullptr;
+        check(b200zk_dev_alloc(&g, p.n_ * 96));
+        check(b200zk_dev_alloc(&gl, p.n_ * 96));
+        int32_t rc = b200zk_srs_generate_dev(s.data(), k, omega.data(), g, gl, nullptr);
+        if (rc == B200ZK_OK) rc = b200zk_bases_register_dev(g, p.n_, B200ZK_FMT_MONT, 96, &p.g_);
+        if (rc == B200ZK_OK) rc = b200zk_bases_register_dev(gl, p.n_, B200ZK_FMT_MONT, 96, &p.gl_);
+        b200zk_dev_free(g);
+        b200zk_dev_free(gl);
+        check(rc);
+        return p;
+    }
+    ParamsKZG(ParamsKZG&& o) noexcept : k_(o.k_), n_(o.n_), g_(o.g_), gl_(o.gl_) { o.g_ = o.gl_ = 0; }
     ~ParamsKZG() {
         if (g_) b200zk_bases_release(g_);
         if (gl_) b200zk_bases_release(gl_);
@@ -54,6 +70,7 @@ public:
     uint64_t g_lagrange() const { return gl_; }
 
 private:
+    explicit ParamsKZG(uint32_t k) : k_(k), n_(uint64_t(1) << k) {}
     uint32_t k_;
     uint64_t n_, g_ = 0, gl_ = 0;
 };

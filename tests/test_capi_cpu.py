@@ -120,7 +120,8 @@ def test_cpp_header_mirror_compiles_and_fails_loudly(zk):
         'int main() {\n'
         '    using namespace b200zk;\n'
         '    try { init(); } catch (const Error& e) { return e.code == B200ZK_ERR_NO_DEVICE ? 42 : 1; }\n'
-        '    DeviceFr v(std::vector<Fr>(8)); auto q = poly::kate_div(v, Fr{}); (void)q; return 0;\n'
+        '    DeviceFr v(std::vector<Fr>(8)); auto q = poly::kate_div(v, Fr{}); (void)q;\n'
+        '    Fr s{}; s[0] = 5; Fr w{}; w[0] = 1; auto pk = ParamsKZG::unsafe_setup(0, s, w); (void)pk; return 0;\n'
         '}\n')
     libdir = os.path.join(ROOT, "plutus-halo2-verifier-gen_b200")
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", libdir, "-lb200zk",
