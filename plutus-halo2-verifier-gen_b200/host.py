@@ -500,6 +500,32 @@ def compile_gates(gates: Sequence[tuple], n_columns: int, y_challenge: Optional[
         if src >> 28 == 1 and (src & 0x0FFFFFFF) != 0:
             free.append(src & 0x0FFFFFFF)
 
+    need_cache: dict = {}
+
+    def need(e) -> int:
+        """Registers needed to evaluate e when the hungrier operand goes first (Sethi-Ullman numbering)."""
+        key = id(e)
+        if key not in need_cache:
+            kind = e[0]
+            if kind in ("const", "challenge", "query"):
+                v = 0
+            elif kind in ("neg", "scaled"):
+                v = max(need(e[1]), 1)
+            else:
+                a, b = need(e[1]), need(e[2])
+                v = max(a, b) if a != b else a + 1
+                v = max(v, 1)
+            need_cache[key] = v
+        return need_cache[key]
+
+    def go2(x, y):
+        """Evaluates two operands, the one that needs more registers first; returns their sources in (x, y) order."""
+        if need(y) > need(x):
+            sy = go(y)
+            return go(x), sy
+        sx = go(x)
+        return sx, go(y)
+
     def go(e):
         """Returns a source operand holding the value of e (a leaf is used in place, anything else lands in a register)."""
         kind = e[0]
@@ -526,13 +552,18 @@ def compile_gates(gates: Sequence[tuple], n_columns: int, y_challenge: Optional[
         if kind in ("sum", "product"):
             # a*b + c in one instruction when a sum has a product on one side
             if kind == "sum" and e[1][0] == "product":
-                x, y_, z = go(e[1][1]), go(e[1][2]), go(e[2])
+                if need(e[2]) > need(e[1]):
+                    z = go(e[2])
+                    x, y_ = go2(e[1][1], e[1][2])
+                else:
+                    x, y_ = go2(e[1][1], e[1][2])
+                    z = go(e[2])
                 for s_ in (x, y_, z):
                     release(s_)
                 d = alloc()
                 emit("muladd", d, x, y_, z)
                 return (1 << 28) | d
-            a, b = go(e[1]), go(e[2])
+            a, b = go2(e[1], e[2])
             release(a)
             release(b)
             d = alloc()

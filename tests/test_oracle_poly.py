@@ -143,3 +143,81 @@ def test_c_oracle_polynomial_side_matches_bigint_oracle(oracle, pyref):
     polys = [[rng.randrange(R) for _ in range(40)] for _ in range(5)]
     cs = [rng.randrange(R) for _ in range(5)]
     assert ti(oracle.lincomb(b"".join(tb(p) for p in polys), tb(cs), 5)) == pyref.lincomb(polys, cs)
+
+
+def test_compile_gates_random_trees(zk, pyref):
+    """Random expression trees (hypothesis): the compiled register program evaluates to the tree's value at every row,
+    never reads a register before writing it, and stays inside the register file."""
+    from hypothesis import given, settings, strategies as st
+
+    leaf = st.one_of(
+        st.tuples(st.just("const"), st.integers(0, R - 1)),
+        st.tuples(st.just("challenge"), st.integers(0, 2)),
+        st.tuples(st.just("query"), st.integers(0, 3), st.integers(-2, 2)),
+    )
+    tree = st.recursive(
+        leaf,
+        lambda ch: st.one_of(
+            st.tuples(st.just("neg"), ch),
+            st.tuples(st.just("scaled"), ch, st.integers(0, R - 1)),
+            st.tuples(st.just("sum"), ch, ch),
+            st.tuples(st.just("product"), ch, ch),
+        ),
+        max_leaves=24,
+    )
+    rng = random.Random(17)
+    k = 3
+    n = 1 << k
+    cols = [[rng.randrange(R) for _ in range(n)] for _ in range(4)]
+    challenges = {0: rng.randrange(R), 1: rng.randrange(R), 2: rng.randrange(R)}
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(tree, min_size=1, max_size=3), st.booleans())
+    def check(gates, fold):
+        cg = zk.host.compile_gates(gates, 4, y_challenge=0 if fold else None)
+        consts = list(cg.consts)
+        for ci, slot in cg.challenge_slots.items():
+            consts[slot] = challenges[ci]
+        prog = [(cg.words[4 * i] & 0xFF, cg.words[4 * i] >> 8, cg.words[4 * i + 1], cg.words[4 * i + 2], cg.words[4 * i + 3])
+                for i in range(len(cg.words) // 4)]
+        written = set()
+        for (op, dst, a, b, c) in prog:
+            nsrc = 1 if op in (3, 4, 5, 7) else (3 if op == 6 else 2)
+            for sref in (a, b, c)[:nsrc]:
+                if sref >> 28 == 1:
+                    assert (sref & 0x0FFFFFFF) in written
+            assert dst < zk.host.GATE_MAX_REGS
+            written.add(dst)
+        got = pyref.gate_eval(prog, consts, cg.rotations, cols, k, k)
+        for row in range(n):
+            vals = [_eval_expr(g, cols, row, n, challenges) for g in gates]
+            if fold:
+                want = 0
+                for v in vals:
+                    want = (want * challenges[0] + v) % R
+            else:
+                want = sum(vals) % R
+            assert got[row] == want
+
+    check()
+
+
+def test_compile_gates_register_allocation(zk, pyref):
+    """Operands are evaluated hungrier-first, so a long one-sided chain (the shape of a y-folded gate list or a Horner
+    form) needs two registers whatever its depth, and a complete binary tree of depth d needs d."""
+    e = ("query", 0, 0)
+    for _ in range(200):
+        e = ("product", ("sum", ("query", 0, 0), ("const", 3)), ("sum", ("const", 5), e))
+    cg = zk.host.compile_gates([e], 1)
+    assert max(w >> 8 for w in cg.words[0::4]) <= 3
+    col = [7, 11]
+    prog = [(cg.words[4 * i] & 0xFF, cg.words[4 * i] >> 8, cg.words[4 * i + 1], cg.words[4 * i + 2], cg.words[4 * i + 3])
+            for i in range(len(cg.words) // 4)]
+    got = pyref.gate_eval(prog, cg.consts, cg.rotations, [col], 1, 1)
+    assert got == [_eval_expr(e, [col], r, 2, {}) for r in range(2)]
+
+    def bushy(d):
+        return ("query", 0, 0) if d == 0 else ("product", bushy(d - 1), bushy(d - 1))
+    # a complete binary tree of depth d needs d registers; overflowing the 48-register file would take 2^48 leaves
+    cg = zk.host.compile_gates([bushy(10)], 1)
+    assert max(w >> 8 for w in cg.words[0::4]) <= 10
