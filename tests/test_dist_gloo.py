@@ -126,12 +126,12 @@ def _ntt_worker(rank, world, port, log_n, inverse, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("log_n,inverse", [(6, False), (7, False), (7, True)])
-def test_sharded_ntt_world2(pyref, log_n, inverse):
-    """The exchange / transpose / twiddle logic of dist.ShardedNTT on two gloo ranks, with the checker's transforms standing
-    in for the kernels: the concatenated result equals the checker's transform of the whole vector."""
+@pytest.mark.parametrize("log_n,inverse,world", [(6, False, 2), (7, False, 2), (7, True, 2), (8, False, 4)])
+def test_sharded_ntt_world2(pyref, log_n, inverse, world):
+    """The exchange / transpose / twiddle logic of dist.ShardedNTT on two (and four) gloo ranks, with the checker's
+    transforms standing in for the kernels: the concatenated result equals the checker's transform of the whole vector."""
     import torch.multiprocessing as mp
-    world, port = 2, 29617 + (os.getpid() + log_n + 7 * inverse) % 1000
+    port = 29617 + (os.getpid() + log_n + 7 * inverse + 13 * world) % 1000
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_ntt_worker, args=(r, world, port, log_n, inverse, q)) for r in range(world)]
@@ -146,7 +146,7 @@ def test_sharded_ntt_world2(pyref, log_n, inverse):
     full = [P.splitmix64(1000 + i) * P.splitmix64(7 + i) % P.R_MOD for i in range(n)]
     w = P.omega(log_n)
     want = P.intt(full, w) if inverse else P.ntt(full, w)
-    raw = got[0] + got[1]
+    raw = b"".join(got[r] for r in range(world))
     assert [int.from_bytes(raw[32 * i:32 * i + 32], "little") for i in range(n)] == want
 
 
