@@ -128,3 +128,21 @@ def test_cpp_header_mirror_compiles_and_fails_loudly(zk):
                            "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
     rc = subprocess.run([exe]).returncode
     assert rc == (0 if _has_gpu() else 42)
+
+
+def test_integration_doc_bindings_match_the_header():
+    """Every `pub fn b200zk_*` of the Rust extern blocks in INTEGRATION.md names a function the header declares, with the
+    same number of parameters (the shim cannot be compiled here, so at least its surface must not drift)."""
+    hdr = open(os.path.join(ROOT, "include", "b200zk.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+
+    def arity(params):
+        params = params.strip()
+        return 0 if params in ("", "void") else params.count(",") + 1
+
+    declared = {m.group(1): arity(m.group(2)) for m in re.finditer(r"\b(b200zk_\w+)\s*\(([^;{]*?)\)\s*;", hdr, re.S)}
+    rust = {m.group(1): arity(m.group(2)) for m in re.finditer(r"pub fn (b200zk_\w+)\s*\(([^)]*)\)", doc, re.S)}
+    assert len(rust) >= 25
+    for name, n in rust.items():
+        assert name in declared, "INTEGRATION.md binds %s, which include/b200zk.h does not declare" % name
+        assert declared[name] == n, (name, declared[name], n)
