@@ -146,3 +146,20 @@ def test_integration_doc_bindings_match_the_header():
     for name, n in rust.items():
         assert name in declared, "INTEGRATION.md binds %s, which include/b200zk.h does not declare" % name
         assert declared[name] == n, (name, declared[name], n)
+
+
+def test_ctypes_signatures_match_the_header_arity(zk):
+    """capi.SIGNATURES (the ctypes prototypes every Python call goes through) against the C declarations: same parameter
+    count for every entry point, 64-bit parameters bound as 64-bit."""
+    import ctypes as C
+    hdr = open(os.path.join(ROOT, "include", "b200zk.h")).read()
+    for m in re.finditer(r"\b(?:int32_t|uint64_t)\s+(b200zk_\w+)\s*\(([^;{]*?)\)\s*;", hdr, re.S):
+        name, params = m.group(1), m.group(2).strip()
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        res, args = zk.capi.SIGNATURES[name]
+        assert len(args) == len(plist), (name, len(args), plist)
+        for a, p in zip(args, plist):
+            if re.match(r"^(uint64_t|size_t)\s+\w+$", p):
+                assert a in (C.c_uint64, C.c_size_t), (name, p, a)
+            if re.match(r"^(uint32_t|int32_t)\s+\w+$", p):
+                assert a in (C.c_uint32, C.c_int32), (name, p, a)
