@@ -163,3 +163,11 @@ def test_ctypes_signatures_match_the_header_arity(zk):
                 assert a in (C.c_uint64, C.c_size_t), (name, p, a)
             if re.match(r"^(uint32_t|int32_t)\s+\w+$", p):
                 assert a in (C.c_uint32, C.c_int32), (name, p, a)
+
+
+def test_oracle_files_declare_their_role():
+    """oracle/ is the checker, never the product: both restatements say so in their header, and name what is pinned."""
+    for f in ("pyref.py", "b200zk_oracle.c"):
+        head = open(os.path.join(ROOT, "oracle", f)).read(3000)
+        assert "TEST INFRASTRUCTURE ONLY" in head, f
+    assert "unpinned" in open(os.path.join(ROOT, "oracle", "pyref.py")).read(3000)
