@@ -5,17 +5,18 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 HOSTCXX ?= /usr/bin/g++
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -ccbin $(HOSTCXX) \
            -Iinclude -I$(PKG)/csrc
-SRCS := $(PKG)/csrc/b200zk.cu $(PKG)/csrc/b200zk_ext.cu
+SRCS := $(PKG)/csrc/b200zk.cu $(PKG)/csrc/b200zk_ext.cu $(PKG)/csrc/b200zk_diag.cu $(PKG)/csrc/h2mo.cu
 OBJS := $(SRCS:$(PKG)/csrc/%.cu=build/%.o)
 HDRS := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.hpp) include/b200zk.h
 
 all:
-	$(MAKE) -j2 lib
+	$(MAKE) -j4 lib
 	$(MAKE) oracle
 
 lib: $(PKG)/libb200zk.so
 
-# two translation units (MSM + NTT + context; polynomial side + SRS + decompression) compiled side by side
+# four translation units (MSM + NTT + contexts; polynomial side + SRS + decompression; self-test + micro-benchmarks;
+# transcript + multi-open + guards) compiled side by side
 build/%.o: $(PKG)/csrc/%.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c -o $@ $<

@@ -6,8 +6,8 @@
 
 Metric (BASELINE.json): BLS12-381 G1 MSM points/s on 2^24 synthetic points with uniform scalars
 (distribution "U"); a step is one full MSM.  With N > 1 GPUs the same 2^24
-points are sharded by point range (strong scaling) and the N partial points are all-gathered over
-NVLink and summed on the device.  The Fr NTT at 2^22 is measured in the same run and reported in
+points are sharded by point range (strong scaling) and the N partial sums meet in GPU 0's HBM
+through peer stores issued by the MSM's last kernel (the last arriver folds them).  The Fr NTT at 2^22 is measured in the same run and reported in
 the "ntt" object.  Inputs are resident in HBM for `value`; `e2e` goes through the public host-buffer
 entry points with the host<->device copies inside the timed region.
 
@@ -138,56 +138,104 @@ def load_oracle():
     L.orc_g1_synth_bases.argtypes = [u64, u64, u64, C.c_void_p, C.c_int]
     L.orc_ntt.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
     L.orc_max_threads.restype = C.c_int
+    L.orc_fr_dot_u64.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_void_p]
+    L.orc_g1_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_g1_generator.argtypes = [C.c_void_p]
     return L
 
 
-def cpu_msm_sample(L, log_sample: int, reps: int = 1):
-    """Times the CPU restatement on the first 2^log_sample points of the workload (all host threads)."""
+def host_threads() -> int:
+    """Every host thread the box has: torchrun exports OMP_NUM_THREADS=1 to its ranks, which would silently turn the CPU arm
+    into a single-core run, so the thread count is passed to the oracle explicitly."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def dlog_identity_point(L, scalars_np, seed, start, n):
+    """(sum_i s_i * a_i mod r) * G for the synthetic bases P_i = a_i * G, a_i = splitmix64(seed + start + i): what any correct MSM of
+    the workload must return, computed without touching a single base point (one dot product + one scalar multiplication)."""
     import numpy as np
 
-    n = 1 << log_sample
-    bases = np.empty(96 * n, dtype=np.uint8)
-    L.orc_g1_synth_bases(BASE_SEED, 0, n, bases.ctypes.data, 0)
+    x = (np.arange(start, start + n, dtype=np.uint64) + np.uint64(seed)) + np.uint64(0x9E3779B97F4A7C15)
+    z = x.copy()
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    a = np.ascontiguousarray(z ^ (z >> np.uint64(31)))
+    dot = np.zeros(32, dtype=np.uint8)
+    sc = np.ascontiguousarray(scalars_np)
+    L.orc_fr_dot_u64(sc.ctypes.data, a.ctypes.data, n, dot.ctypes.data)
+    gen = np.zeros(96, dtype=np.uint8)
+    L.orc_g1_generator(gen.ctypes.data)
+    out = np.zeros(96, dtype=np.uint8)
+    L.orc_g1_mul(gen.ctypes.data, dot.ctypes.data, out.ctypes.data)
+    return bytes(out)
+
+
+def cpu_msm(L, log_n: int, threads: int, bases_ptr=None):
+    """One MSM of the first 2^log_n points of the workload on the CPU checker.  bases_ptr: affine wire-format bases already
+    in host memory (else they are synthesised on the CPU).  Returns (seconds, result bytes, scalars)."""
+    import numpy as np
+
+    n = 1 << log_n
+    keep = None
+    if bases_ptr is None:
+        keep = np.empty(96 * n, dtype=np.uint8)
+        L.orc_g1_synth_bases(BASE_SEED, 0, n, keep.ctypes.data, threads)
+        bases_ptr = keep.ctypes.data
     sc = synth_scalars_np(SCALAR_SEED, 0, n)
     out = np.zeros(96, dtype=np.uint8)
-    best = None
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        L.orc_g1_msm(bases.ctypes.data, sc.ctypes.data, n, out.ctypes.data, 0)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n / best, best, bytes(out), bases, sc
+    t0 = time.perf_counter()
+    L.orc_g1_msm(bases_ptr, sc.ctypes.data, n, out.ctypes.data, threads)
+    return time.perf_counter() - t0, bytes(out), sc
 
 
 def run_reference(args):
-    """CPU arm: the oracle port on all host threads, each step a bounded sample of the workload."""
+    """CPU arm: the checker's C port of the path on every host thread.  Timed steps run the FULL workload when K of them fit the
+    time budget (then same_config is true); otherwise each step is the largest power-of-two sample that fits, and the line
+    says so.  Warm-up steps run a 2^20 sample (there is nothing to warm on a CPU; they are not timed)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    L = load_oracle()
-    cores = L.orc_max_threads()
-    log_sample = min(args.cpu_sample_log_n, args.log_n)
     import numpy as np
 
+    L = load_oracle()
+    threads = host_threads()
+    t_probe, _, _ = cpu_msm(L, min(20, args.log_n), threads)
+    est_full = t_probe * (1 << max(0, args.log_n - 20)) * 0.85       # Pippenger: a little cheaper per point at larger n
+    log_sample = args.log_n
+    while log_sample > 16 and est_full * args.steps / (1 << (args.log_n - log_sample)) > args.cpu_budget_s:
+        log_sample -= 1
+    if args.cpu_sample_log_n:
+        log_sample = min(args.cpu_sample_log_n, args.log_n)
     n = 1 << log_sample
     bases = np.empty(96 * n, dtype=np.uint8)
-    L.orc_g1_synth_bases(BASE_SEED, 0, n, bases.ctypes.data, 0)
+    t0 = time.perf_counter()
+    L.orc_g1_synth_bases(BASE_SEED, 0, n, bases.ctypes.data, threads)
+    synth_s = time.perf_counter() - t0
     sc = synth_scalars_np(SCALAR_SEED, 0, n)
     out = np.zeros(96, dtype=np.uint8)
+    nw = 1 << min(20, log_sample)
     for _ in range(args.warmup):
-        L.orc_g1_msm(bases.ctypes.data, sc.ctypes.data, n, out.ctypes.data, 0)
+        L.orc_g1_msm(bases.ctypes.data, sc.ctypes.data, nw, out.ctypes.data, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        L.orc_g1_msm(bases.ctypes.data, sc.ctypes.data, n, out.ctypes.data, 0)
+        L.orc_g1_msm(bases.ctypes.data, sc.ctypes.data, n, out.ctypes.data, threads)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    sample = "first 2^%d of the 2^%d points per step (CPU restatement of Pippenger, not blst)" % (log_sample, args.log_n)
+    same = log_sample == args.log_n
+    parity = dlog_identity_point(L, sc, BASE_SEED, 0, n) == bytes(out)
+    sample = ("the full 2^%d-point workload per timed step" % args.log_n if same else
+              "first 2^%d of the 2^%d points per timed step (K full-size steps exceed the %d s budget)" % (log_sample, args.log_n, args.cpu_budget_s)) + \
+             "; %d host threads; CPU restatement of signed-window Pippenger, not blst; bases synthesised on the CPU in %.0f s (untimed)" % (threads, synth_s)
     line = {
         "impl": "reference", "metric": "g1_msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u64x6 Montgomery (integer)", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, 1), "same_config": same,
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample,
+                         "self_check_dlog_identity": parity},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -196,7 +244,8 @@ def run_reference(args):
 def workload_config(args, n_gpus):
     return {"workload": "BLS12-381 G1 MSM, 2^%d points, uniform 255-bit scalars (distribution U)" % args.log_n,
             "log_n": args.log_n, "bases": "a_i*G, a_i = splitmix64(0xB200 + i)", "scalars": "splitmix64 seed 1, reduced mod r",
-            "sharding": "point-range over %d GPU(s), partial points all-gathered and summed on device" % n_gpus,
+            "sharding": "point-range over %d GPU(s); the per-GPU partial sums meet in GPU 0's HBM through peer stores issued by the "
+                        "MSM's last kernel, the last arriver folds them" % n_gpus,
             "l2": "inputs (%.0f MiB bases + %.0f MiB scalars per GPU) exceed the 126 MB L2" %
                   (96.0 * (1 << args.log_n) / n_gpus / 2**20, 32.0 * (1 << args.log_n) / n_gpus / 2**20),
             "ntt": "Fr NTT 2^%d forward, natural order" % args.ntt_log_n}
@@ -210,9 +259,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=24)
     ap.add_argument("--ntt-log-n", type=int, default=22)
-    ap.add_argument("--cpu-sample-log-n", type=int, default=19)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-sample-log-n", type=int, default=0, help="force the size of the reference arm's timed steps (0 = full size if it fits)")
+    ap.add_argument("--cpu-budget-s", type=int, default=420, help="time budget of the reference arm's timed steps")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (and the full-size oracle parity check)")
     ap.add_argument("--no-ntt", action="store_true")
+    ap.add_argument("--no-circuits", action="store_true", help="skip the proof-shaped replays (BASELINE's create_proof metric)")
+    ap.add_argument("--no-single-process", action="store_true", help="N > 1: skip the one-process-drives-all-GPUs measurement")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: how the partial sums meet")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--acc-variant", type=int, default=-1, help="accumulate-kernel code variant (experiments)")
     ap.add_argument("--no-tables", action="store_true", help="do not build window tables at registration")
@@ -231,12 +284,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")      # host-side waits that must not keep a kernel spinning on the GPUs
     zk = importlib.import_module("plutus-halo2-verifier-gen_b200")
-    from importlib import import_module
-    zdist = import_module("plutus-halo2-verifier-gen_b200.dist")
+    zdist = importlib.import_module("plutus-halo2-verifier-gen_b200.dist")
     zk.init(local_rank)
     lib = zk.lib()
     if args.window_bits or args.acc_variant >= 0 or args.smax or args.no_tables:
@@ -264,13 +318,18 @@ def main():
     zk.capi.check(lib.b200zk_g1_synth_bases_dev(BASE_SEED, start, n_local, d_bases.data_ptr(), stream))
     torch.cuda.synchronize()
     h = C.c_uint64(0)
+    free0 = torch.cuda.mem_get_info()[0]
+    t0 = time.perf_counter()
     zk.capi.check(lib.b200zk_bases_register_dev(d_bases.data_ptr(), n_local, zk.FMT_MONT, 96, C.byref(h)))
+    table_build_ms = (time.perf_counter() - t0) * 1e3
+    table_bytes = free0 - torch.cuda.mem_get_info()[0]
     del d_bases
     torch.cuda.empty_cache()
-    h_sc = torch.from_numpy(synth_scalars_np(SCALAR_SEED, start, n_local).view(np.uint8).reshape(-1)).pin_memory()
+    sc_np = synth_scalars_np(SCALAR_SEED, start, n_local)
+    h_sc = torch.from_numpy(sc_np.view(np.uint8).reshape(-1)).pin_memory()
     d_sc = h_sc.cuda()
     h_out = torch.zeros(96, dtype=torch.uint8).pin_memory()
-    msm = zdist.ShardedMSM(h.value, n_local, rank, world)
+    msm = zdist.ShardedMSM(h.value, n_local, rank, world, exchange=args.exchange)
     zk.capi.set_profiling(True)
 
     # ---------------------------------------------------------------- device-resident timing
@@ -294,33 +353,38 @@ def main():
     value = n_total / (ms_per_step * 1e-3)
     prof = zk.capi.get_profile()                      # phases of the last timed step on this rank
     acc_ms = max_over_ranks(prof.get("accumulate", 0.0))
+    sort_ms = max_over_ranks(prof.get("sort", 0.0))
+    tail_ms = max_over_ranks(prof.get("tail", 0.0))
     result_dev = bytes(msm.d_out.cpu().numpy())
 
-    # ---------------------------------------------------------------- end to end (host buffers)
+    # ---------------------------------------------------------------- end to end (host buffers, public C-ABI call)
+    def e2e_call():
+        if world == 1:
+            zk.capi.check(lib.b200zk_msm_g1(h.value, 0, h_sc.data_ptr(), n_local, 0, h_out.data_ptr()))
+        else:
+            msm.run_host(h_sc, h_out)
+
     for _ in range(2):
-        msm.run_host(h_sc, h_out)
+        e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        msm.run_host(h_sc, h_out)
+        e2e_call()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
     result_e2e = bytes(h_out.numpy())
-    if world == 1:                                     # N = 1: also through the plain C-ABI host entry point
-        out_c = C.create_string_buffer(96)
-        zk.capi.check(lib.b200zk_msm_g1(h.value, 0, h_sc.data_ptr(), n_local, 0, zk.capi.addr(out_c)))
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            zk.capi.check(lib.b200zk_msm_g1(h.value, 0, h_sc.data_ptr(), n_local, 0, zk.capi.addr(out_c)))
-        e2e_s = (time.perf_counter() - t0) / args.steps
-        result_e2e = out_c.raw
     assert result_e2e == result_dev, "host-buffer path and device-resident path disagree"
+    assert not msm.timed_out(), "a rank never delivered its partial sum"
 
     # ---------------------------------------------------------------- integer-pipe peak, measured in this run
     ops, ms = C.c_double(), C.c_double()
     zk.capi.check(lib.b200zk_microbench(7, 4000, C.byref(ops), C.byref(ms)))
     imad_peak = max_over_ranks(ops.value)             # IMAD.WIDE.U32 limb-MACs per second on one GPU
-    achieved = n_local * LMAC_PER_POINT / (acc_ms * 1e-3) if acc_ms else 0.0
+    rows = prof.get("windows") or 0
+    IMAD_PER_MADD = 2611.0                            # 6 products x 289 + 2 squarings x 222 + one fused pair x 433
+    issued = IMAD_PER_MADD * n_local * rows           # IMAD.WIDE the accumulate kernel issues per launch
+    achieved = issued / (acc_ms * 1e-3) if acc_ms else 0.0
+    fixed = n_local * LMAC_PER_POINT / (acc_ms * 1e-3) if acc_ms else 0.0
 
     # ---------------------------------------------------------------- NTT 2^22 (rank 0's GPU; replicas only)
     ntt = None
@@ -328,19 +392,52 @@ def main():
         ntt = bench_ntt(zk, lib, torch, np, args, stream, imad_peak)
     barrier()
 
-    # ---------------------------------------------------------------- CPU baseline + parity on the sample
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    # ---------------------------------------------------------------- parity of the full-size result + CPU baseline
+    parity, cpu = None, None
+    if rank == 0:
         L = load_oracle()
-        log_s = min(args.cpu_sample_log_n, args.log_n)
-        pts_per_s, secs, cpu_pt, _, sc_s = cpu_msm_sample(L, log_s, reps=3)
-        out_c = C.create_string_buffer(96)
-        zk.capi.check(lib.b200zk_msm_g1(h.value, 0, sc_s.ctypes.data, 1 << log_s, 0, zk.capi.addr(out_c)))
-        cpu = {"value": pts_per_s, "unit": "points/s", "cores": L.orc_max_threads(), "kind": "port",
-               "sample": "first 2^%d of the 2^%d points, best of 3 runs (%.1f s each, all host threads); CPU restatement of "
-                         "signed-window Pippenger, not blst" % (log_s, args.log_n, secs),
-               "parity_on_sample": out_c.raw == cpu_pt}
-        assert cpu["parity_on_sample"], "GPU MSM differs from the CPU oracle on the sample"
+        threads = host_threads()
+        full_sc = sc_np if world == 1 else synth_scalars_np(SCALAR_SEED, 0, n_total)
+        t0 = time.perf_counter()
+        want = dlog_identity_point(L, full_sc, BASE_SEED, 0, n_total)
+        parity = {"dlog_identity": want == result_dev, "dlog_identity_s": time.perf_counter() - t0,
+                  "note": "MSM(s, a_i*G) == (sum s_i a_i mod r)*G over all 2^%d points, computed by the CPU checker without the bases" % args.log_n}
+        assert parity["dlog_identity"], "GPU MSM violates the discrete-log identity on the full workload"
+        if world == 1 and not args.no_cpu:
+            # the full workload on the CPU, over the very bases the GPU used (read back from the resident table): the CPU baseline
+            # and an independent full-size parity check in one run
+            pts = np.empty(96 * n_total, dtype=np.uint8)
+            zk.capi.check(lib.b200zk_bases_read(h.value, 0, n_total, pts.ctypes.data))
+            secs, cpu_pt, _ = cpu_msm(L, args.log_n, threads, pts.ctypes.data)
+            del pts
+            parity["oracle_full_msm"] = cpu_pt == result_dev
+            assert parity["oracle_full_msm"], "GPU MSM differs from the CPU oracle on the full workload"
+            cpu = {"value": n_total / secs, "unit": "points/s", "cores": threads, "kind": "port",
+                   "sample": "the full 2^%d-point workload, one run (%.1f s, %d host threads) over the bases read back from the GPU's table; CPU "
+                             "restatement of signed-window Pippenger, not blst" % (args.log_n, secs, threads)}
+        parity["parity_full"] = all(v for k, v in parity.items() if isinstance(v, bool))
+
+    # ---------------------------------------------------------------- proof-shaped replays (BASELINE metric iii)
+    circuits = None
+    if rank == 0 and world == 1 and not args.no_circuits:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import circuit_bench
+        L = None if args.no_cpu else load_oracle()
+        circuits = {"note": "MSM + NTT call trace of one create_proof replayed through the C ABI (the Rust prover cannot run here): "
+                            "host-buffer route and resident route; CPU column = the checker's port, sampled calls scaled by the call counts",
+                    "traces": [circuit_bench.run_circuit(zk, lib, L, name, 3, True, host_threads()) for name in ("atms17", "atms19")]}
+
+    # ---------------------------------------------------------------- N > 1: ONE process driving all N GPUs through the plain C ABI
+    single = None
+    if world > 1 and not args.no_single_process:
+        msm.close()
+        zk.capi.check(lib.b200zk_bases_release(h.value))
+        del d_sc
+        torch.cuda.empty_cache()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            single = bench_single_process(zk, lib, torch, np, args, world, result_dev)
+        dist.barrier(group=cpu_group)                   # the other ranks wait on the CPU, their GPUs are idle
 
     if rank == 0:
         peaks = {}
@@ -356,34 +453,91 @@ def main():
             "clocks": clocks,
             "e2e": {"value": n_total / e2e_s, "unit": "points/s", "h2d_bytes_per_step": 32 * n_total,
                     "d2h_bytes_per_step": 96, "ms_per_step": e2e_s * 1e3,
-                    "timed": "host clock around synchronous public calls (H2D scalars, MSM, exchange, D2H result)"},
+                    "timed": "host clock around synchronous public calls (H2D scalars from pinned memory, MSM, exchange, D2H result)"},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "imad", "kernel": "msm_accumulate_kernel_v6", "achieved": achieved / 1e12,
-                         "peak": imad_peak / 1e12, "unit": "Tlimb-MAC/s", "frac": achieved / imad_peak if imad_peak else None,
+                         "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE/s", "frac": achieved / imad_peak if imad_peak else None,
+                         "note": "achieved = IMAD.WIDE.U32 the kernel issues per launch (2611 per mixed addition x %d points x %d table rows) / "
+                                 "its launch time (CUDA events on the launching stream, last timed step, max over ranks); peak = the "
+                                 "IMAD.WIDE.U32 micro-benchmark run in this process (one limb-MAC per instruction)" % (n_local, rows),
+                         "frac_whole_step": (issued / (ms_per_step * 1e-3)) / imad_peak if imad_peak else None,
+                         "frac_fixed_accounting": fixed / imad_peak if imad_peak else None,
+                         "fixed_accounting_note": "SURVEY 8d's size-independent accounting (48 000 limb-MACs/point = 16 windows x 10 products x 300) / "
+                                                  "accumulate time / peak; exceeds 1 because window tables need only %d rows and the additions are "
+                                                  "cheaper than 10 plain products -- a comparison figure, not a utilisation" % rows,
                          "traffic": ncu_traffic("r01_ncu_msm_accumulate_2p24.json", 1) if (args.log_n == 24 and world == 1) else None,
-                         "traffic_note": "bytes per launch of the accumulate kernel (ncu capture of this command, profiles/); "
-                                         "algorithmic bytes = (96 B base + 4 B entry) x points x rows = %.1f GB"
-                                         % (100.0 * n_local * (prof.get("windows") or 0) / 1e9),
-                         "note": "algorithmic work = %d limb-MACs/point x %d points per launch / accumulate-kernel time "
-                                 "(CUDA events on the launching stream, last timed step, max over ranks); peak = IMAD.WIDE.U32 "
-                                 "micro-benchmark measured in this run; window bits actually used: %s"
-                                 % (LMAC_PER_POINT, n_local, prof.get("window_bits")),
-                         "issued_imad_wide_frac": (2611.0 * n_local * (prof.get("windows") or 0) / (acc_ms * 1e-3)) / imad_peak
-                         if (acc_ms and imad_peak) else None,
-                         "issued_note": "IMAD.WIDE actually issued by the kernel (6 products x 289 + 2 squarings x 222 + one fused pair of products "
-                                        "x 433 per mixed addition, one addition per point and table row) / time / peak: the pipe utilisation; "
-                                        "`frac` above uses the fixed 16-window accounting of SURVEY 8d and exceeds it when window "
-                                        "tables allow fewer rows",
-                         "phases_ms": {k: prof.get(k) for k in ("sort", "accumulate", "tail")},
-                         "hbm_crosscheck_gbs": n_local * 128 / (acc_ms * 1e-3) / 1e9 if acc_ms else None,
+                         "traffic_source": "static_profile: profiles/r01_ncu_msm_accumulate_2p24.json (ncu --set full capture of this command at "
+                                           "commit 246bfb6), not measured in this run",
+                         "algorithmic_bytes": 100.0 * n_local * rows,
+                         "window_bits": prof.get("window_bits"), "table_rows": rows,
+                         "phases_ms": {"sort": sort_ms, "accumulate": acc_ms, "tail": tail_ms},
                          "hbm_peak_gbs": peaks.get("hbm_gbs")},
+            "table": {"build_ms": table_build_ms, "bytes": table_bytes,
+                      "note": "window tables (rows 2^(c*w) * P_i) are built once per registered SRS table and are NOT inside any timed region; "
+                              "a ParamsKZG holds two such tables (g, g_lagrange)"},
+            "parity": parity,
             "cpu_baseline": cpu,
             "ntt": ntt,
+            "circuits": circuits,
+            "single_process": single,
             "result_compressed": zk.host.g1_compress(result_dev).hex(),
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_single_process(zk, lib, torch, np, args, n_gpus, expect):
+    """The path a single-process Rust prover reaches: b200zk_init_devices + plain b200zk_msm_g1 against a table partitioned
+    over all GPUs (worker thread per GPU, peer-store exchange).  Timed on the host clock around the synchronous calls."""
+    zk.shutdown()
+    zk.capi.init_devices(None, n_gpus)
+    n = 1 << args.log_n
+    torch.cuda.set_device(0)
+    d_b = torch.empty(96 * n, dtype=torch.uint8, device="cuda:0")
+    zk.capi.check(lib.b200zk_g1_synth_bases_dev(BASE_SEED, 0, n, d_b.data_ptr(), None))
+    torch.cuda.synchronize()
+    h = C.c_uint64(0)
+    t0 = time.perf_counter()
+    zk.capi.check(lib.b200zk_bases_register_dev(d_b.data_ptr(), n, zk.FMT_MONT | zk.capi.BASES_SHARD, 96, C.byref(h)))
+    build_ms = (time.perf_counter() - t0) * 1e3
+    del d_b
+    torch.cuda.empty_cache()
+    sc = synth_scalars_np(SCALAR_SEED, 0, n)
+    h_sc = torch.from_numpy(sc.view(np.uint8).reshape(-1)).pin_memory()
+    out = C.create_string_buffer(96)
+    for _ in range(3):
+        zk.capi.check(lib.b200zk_msm_g1(h.value, 0, h_sc.data_ptr(), n, 0, zk.capi.addr(out)))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        zk.capi.check(lib.b200zk_msm_g1(h.value, 0, h_sc.data_ptr(), n, 0, zk.capi.addr(out)))
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    ok_host = out.raw == expect
+    # resident: every GPU already holds its slice of the scalars
+    layout, _ = zk.capi.bases_layout(h.value)
+    slices = []
+    for dev, s0, cnt in layout:
+        t = torch.empty(32 * cnt, dtype=torch.uint8, device="cuda:%d" % dev)
+        t.copy_(h_sc[32 * s0:32 * (s0 + cnt)])
+        slices.append(t)
+    for d in range(n_gpus):
+        torch.cuda.synchronize(d)
+    ptrs = (C.c_void_p * len(slices))(*[t.data_ptr() for t in slices])
+    for _ in range(3):
+        zk.capi.check(lib.b200zk_msm_g1_sharded_dev(h.value, C.addressof(ptrs), len(slices), 0, zk.capi.addr(out)))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        zk.capi.check(lib.b200zk_msm_g1_sharded_dev(h.value, C.addressof(ptrs), len(slices), 0, zk.capi.addr(out)))
+    res_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    ok_res = out.raw == expect
+    zk.capi.check(lib.b200zk_bases_release(h.value))
+    assert ok_host and ok_res, "single-process multi-GPU result differs from the per-rank path"
+    return {"n_gpus": n_gpus, "e2e_single_process": {"value": n / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
+                                                     "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 96},
+            "resident_single_process": {"value": n / (res_ms * 1e-3), "unit": "points/s", "ms_per_step": res_ms},
+            "table_build_ms": build_ms, "parity_with_per_rank_path": True,
+            "note": "one process, b200zk_init_devices(%d): b200zk_msm_g1 from pinned host scalars / b200zk_msm_g1_sharded_dev with resident "
+                    "slices; host clock around the synchronous calls (includes the fan-out to the per-GPU worker threads)" % n_gpus}
 
 
 def bench_ntt(zk, lib, torch, np, args, stream, imad_peak):
@@ -427,9 +581,9 @@ def bench_ntt(zk, lib, torch, np, args, stream, imad_peak):
         L = load_oracle()
         buf = synth_scalars_np(NTT_SEED, 0, n)
         t0 = time.perf_counter()
-        L.orc_ntt(buf.ctypes.data, log_n, omega, 0, None, None, 0)
+        L.orc_ntt(buf.ctypes.data, log_n, omega, 0, None, None, host_threads())
         dt = time.perf_counter() - t0
-        cpu = {"value": n / dt, "unit": "elements/s", "cores": L.orc_max_threads(), "kind": "port",
+        cpu = {"value": n / dt, "unit": "elements/s", "cores": host_threads(), "kind": "port",
                "sample": "one full 2^%d transform (%.2f s), CPU restatement of radix-2 NTT" % (log_n, dt)}
     return {
         "metric": "fr_ntt_elements_per_s", "log_n": log_n, "value": n / (ms * 1e-3), "unit": "elements/s", "ms_per_step": ms,

@@ -15,8 +15,12 @@
  * Conventions
  *   - every function returns int32_t: 0 = OK, negative = error class (B200ZK_ERR_*);
  *     b200zk_last_error() returns the text of the calling thread's last failure.
- *   - no exceptions cross the boundary; entry points may be called from any host thread
- *     (calls are serialised on one device context per process: one process per GPU).
+ *   - no exceptions cross the boundary; entry points may be called concurrently from any host thread
+ *     (rayon callers): one process drives every GPU bound by b200zk_init_devices; per GPU two calls
+ *     are in flight at a time, each on its own stream, and no lock is held while a call waits for the GPU.
+ *   - host-buffer MSM / NTT entry points use all bound GPUs; every other host-buffer entry point runs on
+ *     the calling thread's selected GPU (b200zk_set_device); "_dev" entry points run on the GPU that owns
+ *     their pointers.
  *   - there is NO CPU fallback: without a usable B200 every call fails with B200ZK_ERR_NO_DEVICE.
  *
  * Wire formats (little-endian throughout)
@@ -59,6 +63,12 @@ extern "C" {
  * costs (W-1) * n * 96 bytes of HBM once and removes the per-window bucket sets and the window combine
  * from every later MSM against it.                                                                     */
 #define B200ZK_BASES_NO_WINDOW_TABLES 0x100u
+/* With several GPUs bound: partition the table by point range (every GPU holds n / G points; each MSM is reduced
+ * to one partial sum per GPU and the partials meet on the first GPU through peer stores over NVLink), or keep a
+ * full copy on every GPU (the columns of a batch are dealt out, no exchange).  Default: replicate tables of up to
+ * 2 GiB including window rows (n <= 2^20), partition larger ones.                                           */
+#define B200ZK_BASES_SHARD 0x200u
+#define B200ZK_BASES_REPLICATE 0x400u
 
 /* NTT flags */
 #define B200ZK_NTT_INVERSE_SCALE 1u /* multiply the result by 1/n (caller passes omega^-1) */
@@ -67,9 +77,19 @@ extern "C" {
 #define B200ZK_NTT_MONT 8u          /* data is in Montgomery form (in and out); omega/shift stay canonical */
 
 /* ---- lifetime -------------------------------------------------------------------------- */
-/* Binds the process to one GPU (one process per GPU).  device < 0 selects the current device. */
+/* Binds the process to the listed GPUs (1..16 CUDA ordinals; NULL = 0 .. n-1).  The reference prover is ONE process
+ * (/root/reference/examples/simple_mul.rs:39-141; commits at :62,72): every later host-buffer MSM / NTT call
+ * fans out over all of them.  With more than one GPU every pair must have peer access (NVLink / NVSwitch).
+ * A second call is a no-op until b200zk_shutdown.                                                            */
+int32_t b200zk_init_devices(const int32_t *device_ids, int32_t n_devices);
+/* One GPU (also what each rank of a one-process-per-GPU job calls).  device < 0 selects the current device. */
 int32_t b200zk_init(int32_t device);
 int32_t b200zk_shutdown(void);
+int32_t b200zk_device_count(void);
+/* Selects, for the calling thread, which bound GPU (index into the b200zk_init_devices list) serves the entry
+ * points that neither fan out nor take a device pointer (b200zk_dev_alloc, b200zk_msm_g1_adhoc, gate-program
+ * creation, ...).  Default 0.                                                                               */
+int32_t b200zk_set_device(int32_t index);
 int32_t b200zk_last_error(char *buf, size_t len);
 /* name, SM count and compute capability of the bound device, e.g. "NVIDIA B200 sm_100 148SM" */
 int32_t b200zk_device_info(char *buf, size_t len);
@@ -106,6 +126,18 @@ int32_t b200zk_msm_g1(uint64_t bases, uint64_t offset, const uint8_t *scalars, u
  * (one MSM per committed column); scalars = batch*n elements, out = batch*96 bytes.          */
 int32_t b200zk_msm_g1_batch(uint64_t bases, uint64_t offset, const uint8_t *scalars, uint64_t n, uint32_t batch,
                             uint32_t scalar_fmt, uint8_t *out_affine);
+/* The same with one pointer per column: halo2 keeps every polynomial in its own Vec, so the shim passes the Vecs'
+ * addresses and no host-side gather is needed.                                                              */
+int32_t b200zk_msm_g1_batch_ptrs(uint64_t bases, uint64_t offset, const uint8_t *const *scalars, uint64_t n, uint32_t batch,
+                                 uint32_t scalar_fmt, uint8_t *out_affine);
+/* How a table is laid out over the bound GPUs: shard k holds points [start[k], start[k] + n[k]) on GPU index device[k]
+ * (a replicated table reports every shard as [0, n)).  Arrays of `cap` entries; any output may be NULL.           */
+int32_t b200zk_bases_layout(uint64_t bases, uint32_t cap, uint32_t *out_n_shards, int32_t *out_device, uint64_t *out_start,
+                            uint64_t *out_n, uint32_t *out_replicated);
+/* One full-length MSM against a table partitioned over several GPUs, with the scalars already resident: slice k (the
+ * scalars of shard k's points, 16-byte aligned) lives in the HBM of shard k's GPU.  The result comes back to the host. */
+int32_t b200zk_msm_g1_sharded_dev(uint64_t bases, const void *const *d_scalar_slices, uint32_t n_slices, uint32_t scalar_fmt,
+                                  uint8_t out_affine[96]);
 /* Bases that are not resident: the verifier's DualMSM left/right sums
  * (Guard::verify / DualMSM::check, /root/reference/examples/simple_mul.rs:98-102,
  * /root/reference/examples/ivc.rs:196; batch_verify, /root/reference/src/circuits/schnorr_circuit.rs:224).     */
@@ -123,6 +155,21 @@ int32_t b200zk_msm_g1_partial_dev(uint64_t bases, uint64_t offset, const void *d
                                   void *d_out_xyzz, void *stream);
 int32_t b200zk_g1_sum_partials_dev(const void *d_partials_xyzz, uint32_t n, void *d_out_mont, void *d_out_canon,
                                    void *stream);
+/* The same exchange without a collective library (one process per GPU): rank 0 creates the meeting point in its HBM
+ * and hands the 64-byte CUDA-IPC handle to the other ranks, which map it.  b200zk_msm_g1_xchg_dev then runs the local
+ * MSM, stores the XYZZ partial into rank 0's memory from inside its last kernel and bumps an arrival counter with a
+ * system-scope atomic; the rank that arrives last folds the partials and normalises; every rank's call ends with a
+ * short kernel that waits (bounded, ~4 s) for that result and copies it into d_out_*.  Every part must make the same
+ * sequence of calls.  b200zk_xchg_status reports whether a wait ever timed out (a peer never arrived).           */
+int32_t b200zk_xchg_create(uint32_t n_parts, uint8_t out_ipc_handle[64], uint64_t *out_xchg);
+int32_t b200zk_xchg_open(const uint8_t ipc_handle[64], uint32_t n_parts, uint32_t part, uint64_t *out_xchg);
+int32_t b200zk_xchg_close(uint64_t xchg);
+int32_t b200zk_xchg_status(uint64_t xchg, uint32_t *out_timed_out);
+int32_t b200zk_msm_g1_xchg_dev(uint64_t bases, uint64_t offset, const void *d_scalars, uint64_t n, uint32_t scalar_fmt,
+                               uint64_t xchg, void *d_out_mont, void *d_out_canon, void *stream);
+/* host-buffer form: this rank's slice of the scalars streams up in two pieces like b200zk_msm_g1; synchronous */
+int32_t b200zk_msm_g1_xchg(uint64_t bases, uint64_t offset, const uint8_t *scalars, uint64_t n, uint32_t scalar_fmt,
+                           uint64_t xchg, uint8_t out_affine[96]);
 /* Sum of n affine points: combines the per-GPU partial results of a point-range sharded MSM
  * (Montgomery affine in HBM, e.g. the all-gathered d_out_mont of every rank).                */
 int32_t b200zk_g1_sum_dev(const void *d_points_mont, uint32_t n, void *d_out_mont, void *d_out_canon, void *stream);
@@ -138,6 +185,9 @@ int32_t b200zk_ntt_fr(uint8_t *data, uint32_t log_n, const uint8_t omega[32], ui
 /* `batch` polynomials stored back to back (batch * 2^log_n elements) */
 int32_t b200zk_ntt_fr_batch(uint8_t *data, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
                             const uint8_t coset_shift[32]);
+/* one pointer per polynomial (separate Vecs); with several GPUs bound the polynomials are dealt out in blocks */
+int32_t b200zk_ntt_fr_batch_ptrs(uint8_t *const *data, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
+                                 const uint8_t coset_shift[32]);
 int32_t b200zk_ntt_fr_dev(void *d_data, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
                           const uint8_t coset_shift[32], void *stream);
 
@@ -224,6 +274,58 @@ int32_t b200zk_gate_program_run_dev(uint64_t handle, const void *const *d_column
                                     void *stream);
 int32_t b200zk_gate_program_release(uint64_t handle);
 
+/* =============================================================================================
+ * The flows above the kernels, composed inside the library (one call per opening / per batch of proofs).
+ * ============================================================================================= */
+
+/* ---- Fiat-Shamir transcript: CardanoFriendlyBlake2b ------------------------------------------------
+ * Unkeyed blake2b-256 over the whole absorbed history: 0x01 || item per absorbed scalar (32 B LE) or point (48 B
+ * compressed), 0x00 per squeeze; challenge = LE(H) + LE(H(H)) * 2^256 mod r
+ * (/root/reference/src/plutus_gen/adjusted_types/mod.rs:30-72; /root/reference/aiken-verifier/aiken_halo2/lib/transcript.ak:19-106).
+ * Host-side byte logic (no GPU needed).  A verifier "reads" a proof item by absorbing the same bytes.          */
+int32_t b200zk_transcript_new(uint64_t *out_transcript);
+int32_t b200zk_transcript_free(uint64_t transcript);
+int32_t b200zk_transcript_common_scalar(uint64_t transcript, const uint8_t scalar[32]);
+int32_t b200zk_transcript_common_point(uint64_t transcript, const uint8_t compressed[48]);
+int32_t b200zk_transcript_squeeze(uint64_t transcript, uint8_t out_challenge[32]);
+
+/* ---- KZGCommitmentScheme::multi_open, prover side, polynomials resident in HBM ------------------------
+ * The halo2 multi-open argument in the message order the reference pins
+ * (/root/reference/src/plutus_gen/extraction/pcs/kzg.rs:55-79): squeeze x1, x2; write the commitment of
+ * f = sum_s x2^s (q_s - r_s) / Z_s; squeeze x3; write q_s(x3) for every point set; squeeze x4; write the commitment pi of
+ * (final - final(x3)) / (X - x3), final = sum_s x4^s q_s + x4^S f.  q_s = sum_j x1^j p_{s,j} over the polynomials opened at
+ * point set s; sets and their order follow precompute_intermediate_sets (/root/reference/src/plutus_gen/extraction/pcs/mod.rs:36-109).
+ * d_polys: HOST array of device pointers, n Montgomery coefficients each, all on one GPU on which `bases` (the monomial
+ * table g) is resident.  Query i opens polynomial query_poly[i] at query_points[32 i ..].  The transcript is advanced exactly
+ * as the verifier will advance it.  out_proof receives f (48 B) || q evals (32 B each) || pi (48 B); *out_len its length.  */
+int32_t b200zk_h2mo_open_dev(uint64_t bases, uint64_t transcript, const void *const *d_polys, uint32_t n_polys, uint64_t n,
+                             const uint32_t *query_poly, const uint8_t *query_points, uint32_t n_queries, uint8_t *out_proof,
+                             size_t cap, size_t *out_len);
+
+/* ---- KZGCommitmentScheme::multi_prepare, verifier side -------------------------------------------------
+ * Replays the transcript over the opening proof, runs the scalar pipeline of
+ * /root/reference/aiken-verifier/aiken_halo2/lib/halo2_kzg.ak:46-171 (q_eval_sets, f_eval, v) on the host and returns a guard:
+ * the two lazy sums  left = pi,  right = sum_s x4^s sum_j x1^j C_{s,j} + x4^S f - v G + x3 pi  (halo2_kzg.ak:15-44), to be
+ * accepted iff e(left, [s]G2) == e(right, G2).  commitments: 48-byte compressed points; query i says commitment
+ * query_commitment[i] is claimed to evaluate to query_evals[32 i ..] at query_points[32 i ..].  out_scalars (optional, 192 B):
+ * x1, x2, x3, x4, f_eval, v.                                                                                       */
+int32_t b200zk_h2mo_prepare(uint64_t transcript, const uint8_t *commitments, uint32_t n_commitments, const uint32_t *query_commitment,
+                            const uint8_t *query_points, const uint8_t *query_evals, uint32_t n_queries, const uint8_t *proof,
+                            size_t proof_len, uint64_t *out_guard, uint8_t *out_scalars);
+/* The scalar pipeline alone with the four challenges given (x1 || x2 || x3 || x4): the known-answer surface of the reference's
+ * own tests (/root/reference/plinth-verifier/plutus-halo2/src/Plutus/Crypto/Halo2/Halo2MultiOpenMSM.hs:26-42).  out_q_eval_sets:
+ * set after set, the points of a set in ascending canonical order.                                                  */
+int32_t b200zk_h2mo_scalars(uint32_t n_commitments, const uint32_t *query_commitment, const uint8_t *query_points,
+                            const uint8_t *query_evals, uint32_t n_queries, const uint8_t challenges[128], const uint8_t *proof_q_evals,
+                            uint32_t n_sets, uint8_t *out_q_eval_sets, size_t cap_q_eval_sets, uint8_t out_f_eval[32], uint8_t out_v[32]);
+/* Guard::verify / batch_verify up to the pairing (/root/reference/examples/simple_mul.rs:98-102,
+ * /root/reference/src/circuits/schnorr_circuit.rs:224-229): left and right sums of sum_i c_i * guard_i (challenges = NULL: one
+ * guard, c = 1).  Every proof point is decompressed on the GPU in one batch and each side is one ad-hoc MSM, split by point
+ * range over the bound GPUs with the partial sums meeting on the first.                                              */
+int32_t b200zk_guard_eval(const uint64_t *guards, uint32_t n_guards, const uint8_t *challenges, uint8_t out_left[96],
+                          uint8_t out_right[96]);
+int32_t b200zk_guard_free(uint64_t guard);
+
 /* ---- synthetic inputs and self-test (bench / tests) ------------------------------------------
  * bases P_i = a_i*G with a_i = splitmix64(seed + start + i), written as packed Montgomery affine. */
 int32_t b200zk_g1_synth_bases_dev(uint64_t seed, uint64_t start, uint64_t n, void *d_out_mont, void *stream);
@@ -231,7 +333,8 @@ int32_t b200zk_g1_synth_bases_dev(uint64_t seed, uint64_t start, uint64_t n, voi
  * op 0 mul, 1 add, 2 sub, 3 inverse(a); field 0 = Fr (32 B), 1 = Fp (48 B); canonical in/out.    */
 int32_t b200zk_selftest_field(uint32_t field, uint32_t op, const uint8_t *a, const uint8_t *b, uint8_t *out,
                               uint64_t count);
-/* integer-pipe micro-benchmark: kind 0 = independent IMAD.WIDE.U32, 1 = IMAD lo+hi pairs, 2 = Fp Montgomery
+/* integer-pipe micro-benchmark: kind 0 = independent IMAD.WIDE.U32, (1 was removed: ptxas hoisted half of its
+ * pairs, so it timed 32-bit IMADs), 2 = Fp Montgomery
  * multiplications, 3 = XYZZ mixed additions, 4 = Fr multiplications, 5 = carry-chained IMAD.WIDE.U32.X rows
  * (as the Montgomery multiplier issues them), 6 = DFMA, 7 = IMAD.WIDE with carry-out only, 8 = IMAD.WIDE
  * paired 1:1 with IADD, 9 = IMAD.HI.U32 alone, 10 = 32-bit IMAD alone, 11 = the unfused IMAD + IMAD.HI.U32 pair with an

@@ -355,6 +355,87 @@ def h2mo_v(f_eval: int, x4: int, proof_q_evals) -> int:
     return acc
 
 
+def h2mo_sets(queries):
+    """precompute_intermediate_sets (src/plutus_gen/extraction/pcs/mod.rs:36-109) on (polynomial, point[, eval]) queries:
+    polynomials in order of first appearance, equal point sets share an index numbered by first appearance.
+    Returns (point_sets, members, evals_by_poly) with the points of a set in ascending order."""
+    per, order = {}, []
+    for q in queries:
+        p, x = q[0], q[1] % R_MOD
+        if p not in per:
+            per[p] = {}
+            order.append(p)
+        if len(q) > 2:
+            per[p][x] = q[2] % R_MOD
+        else:
+            per[p].setdefault(x, None)
+    point_sets, members, evals = [], [], {}
+    for p in order:
+        key = sorted(per[p])
+        if key not in point_sets:
+            point_sets.append(key)
+            members.append([])
+        members[point_sets.index(key)].append(p)
+        evals[p] = [per[p][x] for x in key]
+    return point_sets, members, evals
+
+
+def poly_interpolate(points):
+    """Coefficients (low to high) of the polynomial through (xi, yi)."""
+    coef = [0] * len(points)
+    for i, (xi, yi) in enumerate(points):
+        num, den = [1], 1
+        for j, (xj, _) in enumerate(points):
+            if j != i:
+                num = [(a - xj * b) % R_MOD for a, b in zip([0] + num, num + [0])]
+                den = den * (xi - xj) % R_MOD
+        sc = yi * fr_inv(den) % R_MOD
+        for d, c in enumerate(num):
+            coef[d] = (coef[d] + sc * c) % R_MOD
+    return coef
+
+
+def h2mo_open(polys, queries, transcript: "Transcript", commit):
+    """Prover side of the halo2 multi-open in the message order of src/plutus_gen/extraction/pcs/kzg.rs:55-79 (X1, X2,
+    FCommitment, X3, QEvals, X4, PI), on coefficient lists with big integers.  `commit` maps a coefficient list to a G1
+    point.  Returns the proof bytes f || q_evals || pi."""
+    n = len(polys[0])
+    point_sets, members, _ = h2mo_sets(queries)
+    x1 = transcript.squeeze()
+    qs = []
+    for mem in members:
+        acc, xp = [0] * n, 1
+        for p in mem:
+            acc = [(a + xp * c) % R_MOD for a, c in zip(acc, polys[p])]
+            xp = xp * x1 % R_MOD
+        qs.append(acc)
+    x2 = transcript.squeeze()
+    f, xp = [0] * n, 1
+    for pts, q in zip(point_sets, qs):
+        r = poly_interpolate([(x, poly_eval(q, x)) for x in pts])
+        g = [(c - (r[i] if i < len(r) else 0)) % R_MOD for i, c in enumerate(q)]
+        for x in pts:
+            g, rem = kate_div(g, x)
+            assert rem == 0
+        f = [(a + xp * (g[i] if i < len(g) else 0)) % R_MOD for i, a in enumerate(f)]
+        xp = xp * x2 % R_MOD
+    f_pt = commit(f)
+    transcript.common_point(f_pt)
+    x3 = transcript.squeeze()
+    q_evals = [poly_eval(q, x3) for q in qs]
+    for e in q_evals:
+        transcript.common_scalar(e)
+    x4 = transcript.squeeze()
+    final, xp = [0] * n, 1
+    for q in qs + [f]:
+        final = [(a + xp * c) % R_MOD for a, c in zip(final, q)]
+        xp = xp * x4 % R_MOD
+    w, _v = kate_div(final, x3)
+    pi_pt = commit(w)
+    transcript.common_point(pi_pt)
+    return g1_compress(f_pt) + b"".join(fr_to_le(e) for e in q_evals) + g1_compress(pi_pt)
+
+
 # --------------------------------------------------------------------------- synthetic inputs
 def splitmix64(x: int) -> int:
     x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF

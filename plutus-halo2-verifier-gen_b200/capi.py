@@ -11,6 +11,9 @@ import threading
 
 FMT_CANONICAL = 0
 FMT_MONT = 1
+BASES_NO_WINDOW_TABLES = 0x100
+BASES_SHARD = 0x200
+BASES_REPLICATE = 0x400
 NTT_INVERSE_SCALE = 1
 NTT_COSET_IN = 2
 NTT_COSET_OUT = 4
@@ -39,7 +42,10 @@ def lib_path() -> str:
 # can walk it against include/b200zk.h
 _u8p = C.c_void_p  # byte buffers are passed as raw addresses (bytes, bytearray, numpy, torch all work)
 SIGNATURES = {
+    "b200zk_init_devices": (C.c_int32, [C.c_void_p, C.c_int32]),
     "b200zk_init": (C.c_int32, [C.c_int32]),
+    "b200zk_device_count": (C.c_int32, []),
+    "b200zk_set_device": (C.c_int32, [C.c_int32]),
     "b200zk_shutdown": (C.c_int32, []),
     "b200zk_last_error": (C.c_int32, [C.c_char_p, C.c_size_t]),
     "b200zk_device_info": (C.c_int32, [C.c_char_p, C.c_size_t]),
@@ -51,14 +57,26 @@ SIGNATURES = {
     "b200zk_bases_read": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint64, _u8p]),
     "b200zk_msm_g1": (C.c_int32, [C.c_uint64, C.c_uint64, _u8p, C.c_uint64, C.c_uint32, _u8p]),
     "b200zk_msm_g1_batch": (C.c_int32, [C.c_uint64, C.c_uint64, _u8p, C.c_uint64, C.c_uint32, C.c_uint32, _u8p]),
+    "b200zk_msm_g1_batch_ptrs": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, _u8p]),
+    "b200zk_bases_layout": (C.c_int32, [C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_uint32)]),
+    "b200zk_msm_g1_sharded_dev": (C.c_int32, [C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, _u8p]),
     "b200zk_msm_g1_adhoc": (C.c_int32, [_u8p, C.c_uint32, _u8p, C.c_uint32, C.c_uint64, _u8p]),
     "b200zk_msm_g1_dev": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200zk_msm_g1_partial_dev": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "b200zk_g1_sum_partials_dev": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200zk_xchg_create": (C.c_int32, [C.c_uint32, _u8p, C.POINTER(C.c_uint64)]),
+    "b200zk_xchg_open": (C.c_int32, [_u8p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "b200zk_xchg_close": (C.c_int32, [C.c_uint64]),
+    "b200zk_xchg_status": (C.c_int32, [C.c_uint64, C.POINTER(C.c_uint32)]),
+    "b200zk_msm_g1_xchg_dev": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]),
+    "b200zk_msm_g1_xchg": (C.c_int32, [C.c_uint64, C.c_uint64, _u8p, C.c_uint64, C.c_uint32, C.c_uint64, _u8p]),
     "b200zk_g1_sum_dev": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200zk_ntt_fr": (C.c_int32, [_u8p, C.c_uint32, _u8p, C.c_uint32, _u8p]),
     "b200zk_ntt_fr_batch": (C.c_int32, [_u8p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, _u8p]),
+    "b200zk_ntt_fr_batch_ptrs": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, _u8p]),
     "b200zk_ntt_fr_dev": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, _u8p, C.c_void_p]),
     "b200zk_g1_compress": (C.c_int32, [_u8p, _u8p]),
     "b200zk_dev_alloc": (C.c_int32, [C.POINTER(C.c_void_p), C.c_size_t]),
@@ -83,6 +101,18 @@ SIGNATURES = {
     "b200zk_gate_program_set_const": (C.c_int32, [C.c_uint64, C.c_uint32, _u8p]),
     "b200zk_gate_program_run_dev": (C.c_int32, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "b200zk_gate_program_release": (C.c_int32, [C.c_uint64]),
+    "b200zk_transcript_new": (C.c_int32, [C.POINTER(C.c_uint64)]),
+    "b200zk_transcript_free": (C.c_int32, [C.c_uint64]),
+    "b200zk_transcript_common_scalar": (C.c_int32, [C.c_uint64, _u8p]),
+    "b200zk_transcript_common_point": (C.c_int32, [C.c_uint64, _u8p]),
+    "b200zk_transcript_squeeze": (C.c_int32, [C.c_uint64, _u8p]),
+    "b200zk_h2mo_open_dev": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, _u8p, C.c_uint32, _u8p,
+                                         C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b200zk_h2mo_prepare": (C.c_int32, [C.c_uint64, _u8p, C.c_uint32, C.c_void_p, _u8p, _u8p, C.c_uint32, _u8p, C.c_size_t,
+                                        C.POINTER(C.c_uint64), _u8p]),
+    "b200zk_h2mo_scalars": (C.c_int32, [C.c_uint32, C.c_void_p, _u8p, _u8p, C.c_uint32, _u8p, _u8p, C.c_uint32, _u8p, C.c_size_t, _u8p, _u8p]),
+    "b200zk_guard_eval": (C.c_int32, [C.c_void_p, C.c_uint32, _u8p, _u8p, _u8p]),
+    "b200zk_guard_free": (C.c_int32, [C.c_uint64]),
     "b200zk_g1_synth_bases_dev": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "b200zk_selftest_field": (C.c_int32, [C.c_uint32, C.c_uint32, _u8p, _u8p, _u8p, C.c_uint64]),
     "b200zk_microbench": (C.c_int32, [C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -144,6 +174,33 @@ def addr(buf) -> int:
 
 def init(device: int = -1) -> None:
     check(lib().b200zk_init(device))
+
+
+def init_devices(device_ids=None, n: int = 0) -> None:
+    """Binds several GPUs to this process (b200zk_init_devices): ``device_ids`` CUDA ordinals, or the first ``n``."""
+    if device_ids is None:
+        check(lib().b200zk_init_devices(None, n))
+    else:
+        arr = (C.c_int32 * len(device_ids))(*device_ids)
+        check(lib().b200zk_init_devices(C.addressof(arr), len(device_ids)))
+
+
+def bases_layout(handle: int):
+    """[(device index, start, n), ...] and whether the table is replicated."""
+    cnt, rep = C.c_uint32(0), C.c_uint32(0)
+    dev = (C.c_int32 * 16)()
+    start = (C.c_uint64 * 16)()
+    num = (C.c_uint64 * 16)()
+    check(lib().b200zk_bases_layout(handle, 16, C.byref(cnt), C.addressof(dev), C.addressof(start), C.addressof(num), C.byref(rep)))
+    return [(dev[i], start[i], num[i]) for i in range(cnt.value)], bool(rep.value)
+
+
+def device_count() -> int:
+    return int(lib().b200zk_device_count())
+
+
+def set_device(index: int) -> None:
+    check(lib().b200zk_set_device(index))
 
 
 def shutdown() -> None:

@@ -1,17 +1,31 @@
-// b200zk.cu -- device context, workspace management and the C ABI of include/b200zk.h.
-// One process drives one B200; every entry point is serialised on the context mutex and
-// issues its kernels on the caller's stream (the "_dev" variants) or on the context stream.
+// b200zk.cu -- device contexts, workspaces and the C ABI of include/b200zk.h for the hot path:
+// base-table residency, the G1 MSM and the Fr NTT.
+//
+// One process drives every GPU bound by b200zk_init_devices (the reference prover is a single process:
+// /root/reference/examples/simple_mul.rs:39-141 calls commit at :62,72).  Per GPU there is one context with
+// NSLOT workspace slots; a slot is one in-flight MSM or NTT with its own stream, so two host threads (rayon
+// callers) overlap on one GPU -- the memory-bound sort of one call runs under the integer-bound bucket
+// accumulation of the other -- and no lock is held while a call waits for the device.  A base table is
+// either replicated on every GPU (small SRS: the columns of a batch are dealt out, no exchange) or sharded by
+// point range (large SRS: every GPU reduces its slice to one XYZZ partial, the partials meet on the first GPU
+// through peer stores fused into the last kernel of the MSM, msm.cuh).  Host-side fan-out uses one worker
+// thread per GPU so that copies from pageable memory and kernel launches of different GPUs do not serialise.
 // There is no CPU fallback anywhere in this file: without a device the calls fail.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "b200zk.h"
@@ -22,11 +36,12 @@
 #include "ntt.cuh"
 
 using namespace b200zk;
+using b200zk_ctx::DeviceScope;
 
 namespace {
 
 thread_local std::string t_err;
-std::mutex g_mu;
+thread_local int t_dev_index = 0;          // b200zk_set_device
 std::atomic<uint64_t> g_launches{0};
 
 int32_t fail(int32_t code, const std::string& msg) {
@@ -72,12 +87,40 @@ struct DevBuf {
     }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
+struct PinBuf {   // pinned host staging for small results: a D2H copy into it never blocks the enqueuing thread
+    void* p = nullptr;
+    size_t cap = 0;
+    int32_t ensure(size_t bytes) {
+        if (bytes <= cap) return B200ZK_OK;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = std::max<size_t>(bytes * 2, 4096);
+        CU(cudaHostAlloc(&p, want, cudaHostAllocPortable));
+        cap = want;
+        return B200ZK_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
 
 struct BaseTable {
     uint32_t* d = nullptr;  // packed Montgomery affine, 24 limbs per point; `rows` rows of n points
     uint64_t n = 0;
     uint32_t rows = 1;      // > 1: window tables, row w = 2^(c*w) * row 0
     uint32_t c = 0;         // window bits the rows were built for
+};
+// A registered table as the process sees it: replicated (every shard holds all n points) or partitioned by point range.
+struct TableShard {
+    int dev = 0;            // index into the bound devices
+    uint64_t start = 0, n = 0;
+    BaseTable t;
+};
+struct TableSet {
+    uint64_t n = 0;
+    bool replicated = false;
+    std::vector<TableShard> shards;
 };
 
 struct NttPlan {
@@ -105,83 +148,338 @@ struct CosetKey {
     }
 };
 
-struct Ctx {
-    bool inited = false;
-    int device = -1;
-    cudaStream_t stream = nullptr;
-    cudaDeviceProp prop{};
-    std::map<uint64_t, BaseTable> tables;
-    uint64_t next_handle = 1;
-    std::map<NttKey, NttPlan> ntt_plans;
-    std::map<CosetKey, uint32_t*> coset_tables;
-    uint32_t* fixed_table = nullptr;  // 8 x 256 multiples of G for the synthetic-base generator
-    uint32_t tune_c = 0, tune_smax = 0, tune_variant = 6, tune_no_tables = 0;
-    // phase timing (b200zk_set_profiling): events recorded on the launching stream
-    bool profiling = false;
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int ev_count = 0;   // events recorded by the last profiled call
-    int ev_kind = 0;    // 1 = msm, 2 = ntt
-    MsmPlan last_plan{};
-    // MSM workspace
-    DevBuf scalars, counts, offsets, cursor, ntask, task_off, entries, task_bucket, task_start, task_len, buckets,
-        partials, len_hist, len_off, order, heavy, heavy_items, adhoc, buckets2, aff_a, aff_b, aff_pre, redS[2], redA[2], scan_tmp[2], out_mont, out_canon, stage, flag;
-    // NTT workspace
-    DevBuf ntt_data, ntt_tmp[2], small;
-    // second stream + events for host-buffer MSMs that stream their scalars in two halves
-    cudaStream_t copy_stream = nullptr, down_stream = nullptr;
-    std::vector<cudaEvent_t> pipe_up, pipe_done;
+// one in-flight MSM or NTT: stream, scratch, staging
+constexpr int NSLOT = 2;
+struct Slot {
+    int id = 0;
+    bool busy = false;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, down_stream = nullptr;
     cudaEvent_t copy_ev[2] = {nullptr, nullptr};
-    // cross-stream ordering of the shared workspaces
+    std::vector<cudaEvent_t> pipe_up, pipe_done;
+    // MSM workspace
+    DevBuf scalars, counts, offsets, cursor, ntask, task_off, entries, task_bucket, task_start, task_len, buckets, partials, len_hist,
+        len_off, order, heavy, heavy_items, adhoc, buckets2, aff_a, aff_b, aff_pre, redS[2], redA[2], scan_tmp[2], out_mont, out_canon,
+        stage, flag;
+    // NTT workspace
+    DevBuf ntt_data, ntt_tmp[2];
+    PinBuf h_out;
+    // a "_dev" caller's stream is ordered against the previous user of the slot's scratch
     cudaEvent_t ws_event = nullptr;
     cudaStream_t ws_stream = nullptr;
     bool ws_used = false;
+    // phase timing (b200zk_set_profiling): events recorded on the launching stream
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int ev_count = 0, ev_kind = 0;   // kind 1 = msm, 2 = ntt
+    MsmPlan last_plan{};
+    std::vector<DevBuf*> all() {
+        return {&scalars, &counts, &offsets, &cursor, &ntask, &task_off, &entries, &task_bucket, &task_start, &task_len, &buckets,
+                &partials, &len_hist, &len_off, &order, &heavy, &heavy_items, &adhoc, &buckets2, &aff_a, &aff_b, &aff_pre, &redS[0],
+                &redS[1], &redA[0], &redA[1], &scan_tmp[0], &scan_tmp[1], &out_mont, &out_canon, &stage, &flag, &ntt_data, &ntt_tmp[0],
+                &ntt_tmp[1]};
+    }
 };
-Ctx g;
 
-int32_t prof_mark(int idx, cudaStream_t s) {
-    if (!g.profiling) return B200ZK_OK;
-    if (!g.ev[idx]) CU(cudaEventCreate(&g.ev[idx]));
-    CU(cudaEventRecord(g.ev[idx], s));
-    g.ev_count = idx + 1;
-    return B200ZK_OK;
-}
+// host-side fan-out: one worker thread per bound GPU (its CUDA device is set once)
+struct Worker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    bool stop = false;
+    void start(int ordinal) {
+        th = std::thread([this, ordinal] {
+            cudaSetDevice(ordinal);
+            for (;;) {
+                std::function<void()> job;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [this] { return stop || !q.empty(); });
+                    if (q.empty()) return;
+                    job = std::move(q.front());
+                    q.pop_front();
+                }
+                job();
+            }
+        });
+    }
+    void post(std::function<void()> fn) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            q.push_back(std::move(fn));
+        }
+        cv.notify_one();
+    }
+    void shutdown() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_one();
+        if (th.joinable()) th.join();
+    }
+};
 
-// The MSM / NTT workspaces are shared by every call of the process.  Calls on one stream are ordered by the
-// stream itself; when a call arrives on a different stream than the previous one, that stream is made to wait
-// for the previous call's last kernel, so callers may use any stream without racing on the workspaces.
-int32_t ws_enter(cudaStream_t s) {
-    if (!g.ws_event) CU(cudaEventCreateWithFlags(&g.ws_event, cudaEventDisableTiming));
-    if (g.ws_used && s != g.ws_stream) CU(cudaStreamWaitEvent(s, g.ws_event, 0));
-    return B200ZK_OK;
-}
-int32_t ws_leave(cudaStream_t s) {
-    CU(cudaEventRecord(g.ws_event, s));
-    g.ws_stream = s;
-    g.ws_used = true;
-    return B200ZK_OK;
+}  // namespace
+
+namespace b200zk_ctx {
+struct Dev {
+    int ordinal = -1, index = 0;
+    cudaDeviceProp prop{};
+    std::mutex mu;                    // caches below, slot bookkeeping
+    std::mutex gen_mu;                // d_gen only
+    std::condition_variable cv;       // a slot became free
+    Slot slots[NSLOT];
+    unsigned rr = 0;
+    cudaStream_t stream = nullptr;    // registration, table read-back, ext-TU host entry points
+    std::map<NttKey, NttPlan> ntt_plans;
+    std::map<CosetKey, uint32_t*> coset_tables;
+    uint32_t* fixed_table = nullptr;  // 8 x 256 multiples of G for the synthetic-base generator
+    uint32_t* d_gen = nullptr;        // generator of G1, Montgomery affine
+    bool ntt_attr_set = false;
+    DevBuf reg_stage, reg_flag;
+    cudaEvent_t ws_event = nullptr;   // ordering of the ext-TU scratch
+    cudaStream_t ws_stream = nullptr;
+    bool ws_used = false;
+    Worker worker;
+};
+}  // namespace b200zk_ctx
+using Ctx = b200zk_ctx::Dev;
+
+namespace {
+
+std::mutex g_mu;                                   // init / shutdown / tuning / profiling selection
+// bound devices, in b200zk_init_devices order.  Heap-allocated and never destroyed: a process may exit without calling
+// b200zk_shutdown, and static destruction must not touch worker threads or a CUDA runtime that is already gone.
+std::vector<std::unique_ptr<Ctx>>& g_devs = *new std::vector<std::unique_ptr<Ctx>>();
+std::mutex g_tab_mu;
+std::map<uint64_t, std::shared_ptr<TableSet>>& g_tables = *new std::map<uint64_t, std::shared_ptr<TableSet>>();
+uint64_t g_next_handle = 1;
+std::vector<void (*)()> g_hooks;
+// tuning overrides (b200zk_set_msm_tuning) and environment switches, read once
+uint32_t g_tune_c = 0, g_tune_smax = 0, g_tune_variant = 6, g_tune_no_tables = 0;
+bool g_profiling = false;
+Ctx* g_prof_ctx = nullptr;
+Slot* g_prof_slot = nullptr;
+int g_ntt_variant = 1;            // 1: two CTAs per SM (default); 0: one CTA per SM.  B200ZK_NTT_VARIANT overrides.
+int64_t g_chunk_min = 1ll << 23;  // a single host-buffer MSM of at least this many points streams its scalars in two pieces
+size_t g_batch_stream_min = (size_t)128 << 20;
+int64_t g_ntt_pipe_min = 32ll << 20;
+int g_scatter_passes_env = 0;
+uint64_t g_replicate_max_bytes = (uint64_t)2 << 30;   // tables up to this size (with window rows) are replicated on every GPU
+uint64_t g_range_split_min = 1ull << 16;              // single MSMs with at least this many points are split by point range over the GPUs
+
+void read_env() {
+    if (const char* v = getenv("B200ZK_NTT_VARIANT")) g_ntt_variant = atoi(v);
+    if (const char* v = getenv("B200ZK_MSM_CHUNK_MIN")) g_chunk_min = atoll(v);
+    if (const char* v = getenv("B200ZK_BATCH_STREAM_MIN_BYTES")) { g_batch_stream_min = (size_t)atoll(v); if (!g_batch_stream_min) g_batch_stream_min = 1; }
+    if (const char* v = getenv("B200ZK_NTT_PIPE_MIN_BYTES")) g_ntt_pipe_min = atoll(v);
+    if (const char* v = getenv("B200ZK_SCATTER_PASSES")) g_scatter_passes_env = atoi(v);
+    if (const char* v = getenv("B200ZK_REPLICATE_MAX_BYTES")) g_replicate_max_bytes = (uint64_t)atoll(v);
+    if (const char* v = getenv("B200ZK_RANGE_SPLIT_MIN")) g_range_split_min = (uint64_t)atoll(v);
 }
 
 int32_t need_init() {
-    if (!g.inited) return fail(B200ZK_ERR_NOT_INIT, "b200zk_init has not been called (or failed): no CUDA device is bound");
+    if (g_devs.empty()) return fail(B200ZK_ERR_NOT_INIT, "b200zk_init has not been called (or failed): no CUDA device is bound");
     return B200ZK_OK;
+}
+int32_t current_ctx(Ctx** out) {
+    TRY(need_init());
+    int i = t_dev_index;
+    if (i < 0 || i >= (int)g_devs.size()) i = 0;
+    *out = g_devs[i].get();
+    return B200ZK_OK;
+}
+// the bound device that owns a device pointer
+int32_t ctx_for_pointer(const void* p, Ctx** out) {
+    TRY(need_init());
+    if (g_devs.size() == 1 || !p) return current_ctx(out);
+    cudaPointerAttributes pa{};
+    if (cudaPointerGetAttributes(&pa, p) != cudaSuccess || (pa.type != cudaMemoryTypeDevice && pa.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        return fail(B200ZK_ERR_INVALID_ARG, "not a device pointer");
+    }
+    for (auto& d : g_devs)
+        if (d->ordinal == pa.device) { *out = d.get(); return B200ZK_OK; }
+    return fail(B200ZK_ERR_INVALID_ARG, "the pointer lives on a GPU that b200zk_init_devices did not bind");
+}
+
+// ---- slots ---------------------------------------------------------------------------------
+Slot* acquire_slot(Ctx& c) {
+    std::unique_lock<std::mutex> lk(c.mu);
+    for (;;) {
+        for (int k = 0; k < NSLOT; k++) {
+            Slot& s = c.slots[(c.rr + k) % NSLOT];
+            if (!s.busy) {
+                s.busy = true;
+                c.rr = (unsigned)(s.id + 1);
+                return &s;
+            }
+        }
+        c.cv.wait(lk);
+    }
+}
+void release_slot(Ctx& c, Slot* s) {
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        s->busy = false;
+    }
+    c.cv.notify_one();
+}
+struct SlotLease {
+    Ctx* c = nullptr;
+    Slot* s = nullptr;
+    SlotLease() = default;
+    explicit SlotLease(Ctx& ctx) : c(&ctx), s(acquire_slot(ctx)) {}
+    SlotLease(SlotLease&& o) noexcept : c(o.c), s(o.s) { o.s = nullptr; }
+    ~SlotLease() { if (s) release_slot(*c, s); }
+};
+
+int32_t prof_mark(Slot& sl, int idx, cudaStream_t s) {
+    if (!g_profiling) return B200ZK_OK;
+    if (!sl.ev[idx]) CU(cudaEventCreate(&sl.ev[idx]));
+    CU(cudaEventRecord(sl.ev[idx], s));
+    sl.ev_count = idx + 1;
+    return B200ZK_OK;
+}
+void prof_select(Ctx& c, Slot& sl, int kind) {
+    sl.ev_kind = kind;
+    if (!g_profiling) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_prof_ctx = &c;
+    g_prof_slot = &sl;
+}
+
+// A slot's scratch is used by one call at a time on the host side (busy flag); on the device side, a call that arrives
+// on a different stream than the slot's previous user waits for that user's last kernel.
+int32_t ws_enter(Slot& sl, cudaStream_t s) {
+    if (!sl.ws_event) CU(cudaEventCreateWithFlags(&sl.ws_event, cudaEventDisableTiming));
+    if (sl.ws_used && s != sl.ws_stream) CU(cudaStreamWaitEvent(s, sl.ws_event, 0));
+    return B200ZK_OK;
+}
+int32_t ws_leave(Slot& sl, cudaStream_t s) {
+    CU(cudaEventRecord(sl.ws_event, s));
+    sl.ws_stream = s;
+    sl.ws_used = true;
+    return B200ZK_OK;
+}
+int32_t slot_streams(Slot& sl) {
+    if (!sl.copy_stream) {
+        CU(cudaStreamCreateWithFlags(&sl.copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&sl.copy_ev[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&sl.copy_ev[1], cudaEventDisableTiming));
+    }
+    if (!sl.down_stream) CU(cudaStreamCreateWithFlags(&sl.down_stream, cudaStreamNonBlocking));
+    return B200ZK_OK;
+}
+
+// ---- multi-device fan-out ------------------------------------------------------------------
+struct Job {
+    Ctx* c;
+    std::function<int32_t()> fn;
+};
+// Runs every job on its device's worker thread (a single job runs inline with the device made current) and returns the
+// first failure, whose text becomes the calling thread's last error.
+int32_t run_jobs(std::vector<Job>& jobs) {
+    if (jobs.empty()) return B200ZK_OK;
+    if (jobs.size() == 1) {
+        DeviceScope ds(jobs[0].c->ordinal);
+        return jobs[0].fn();
+    }
+    struct Shared {
+        std::mutex mu;
+        std::condition_variable cv;
+        size_t left;
+        std::vector<int32_t> rc;
+        std::vector<std::string> err;
+    } sh;
+    sh.left = jobs.size();
+    sh.rc.assign(jobs.size(), B200ZK_OK);
+    sh.err.resize(jobs.size());
+    for (size_t i = 0; i < jobs.size(); i++) {
+        Job* j = &jobs[i];
+        jobs[i].c->worker.post([j, i, &sh] {
+            int32_t rc = j->fn();
+            std::string e = rc != B200ZK_OK ? t_err : std::string();
+            std::lock_guard<std::mutex> lk(sh.mu);
+            sh.rc[i] = rc;
+            sh.err[i] = std::move(e);
+            if (--sh.left == 0) sh.cv.notify_all();
+        });
+    }
+    std::unique_lock<std::mutex> lk(sh.mu);
+    sh.cv.wait(lk, [&sh] { return sh.left == 0; });
+    for (size_t i = 0; i < jobs.size(); i++)
+        if (sh.rc[i] != B200ZK_OK) return fail(sh.rc[i], "GPU " + std::to_string(jobs[i].c->ordinal) + ": " + sh.err[i]);
+    return B200ZK_OK;
+}
+
+// ---- exchange areas ------------------------------------------------------------------------
+// The meeting point of the per-GPU partial sums of a point-range sharded MSM (msm_combine_kernel): counters,
+// result slots and the gather buffer, in the HBM of a "home" GPU.  In-process areas are reached through peer
+// access; areas shared between processes (one process per GPU, dist.py) through a CUDA-IPC mapping.
+struct XchgArea {
+    uint8_t* base = nullptr;          // device memory on the home GPU (or its IPC mapping)
+    uint32_t* host_canon = nullptr;   // mapped pinned host memory (in-process areas): the result lands here directly
+    uint32_t n_parts = 0, part = 0;
+    bool owner = false, ipc = false, busy = false;
+    bool fetch = false;               // host-buffer calls of a multi-process exchange: wait for the result and read it back
+    int home_ordinal = -1;
+    unsigned long long seq = 0;       // exchanges issued so far (host side)
+    DevBuf status;                    // fetch-kernel status word (multi-process)
+    static size_t bytes() { return (size_t)XCHG_MAX_COLS * (8 + 8 + 96 + 96 + 192 * (size_t)XCHG_MAX_PARTS); }
+    XchgArgs args(uint32_t col0) const {
+        XchgArgs a{};
+        a.arrive = reinterpret_cast<unsigned long long*>(base);
+        a.done = a.arrive + XCHG_MAX_COLS;
+        a.res_mont = reinterpret_cast<uint32_t*>(a.done + XCHG_MAX_COLS);
+        a.res_canon = a.res_mont + 24 * XCHG_MAX_COLS;
+        a.gather = a.res_canon + 24 * XCHG_MAX_COLS;
+        a.host_canon = host_canon;
+        a.seq = seq;
+        a.n_parts = n_parts;
+        a.part = part;
+        a.col0 = col0;
+        return a;
+    }
+};
+XchgArea g_areas[NSLOT];              // in-process: one per concurrent multi-GPU call
+std::mutex g_area_mu;
+std::condition_variable g_area_cv;
+std::map<uint64_t, std::unique_ptr<XchgArea>>& g_xchg = *new std::map<uint64_t, std::unique_ptr<XchgArea>>();   // b200zk_xchg_create / _open handles
+uint64_t g_next_xchg = 1;
+
+XchgArea* acquire_area() {
+    std::unique_lock<std::mutex> lk(g_area_mu);
+    for (;;) {
+        for (auto& a : g_areas)
+            if (a.base && !a.busy) { a.busy = true; return &a; }
+        g_area_cv.wait(lk);
+    }
+}
+void release_area(XchgArea* a) {
+    {
+        std::lock_guard<std::mutex> lk(g_area_mu);
+        a->busy = false;
+    }
+    g_area_cv.notify_one();
 }
 
 // ------------------------------------------------------------------------------------------
 // exclusive scan of n u32 values (in -> out), recursive over 2048-element tiles
 // ------------------------------------------------------------------------------------------
-int32_t scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, int level, cudaStream_t s) {
+int32_t scan_u32(Slot& sl, const uint32_t* in, uint32_t* out, uint64_t n, int level, cudaStream_t s) {
     uint64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (tiles <= 1) {
         LAUNCH(scan_tile_kernel, 1, SCAN_THREADS, 0, s, in, out, n, (uint32_t*)nullptr, (const uint32_t*)nullptr);
         return B200ZK_OK;
     }
     if (level >= 2) return fail(B200ZK_ERR_INVALID_ARG, "scan: input too large");
-    TRY(g.scan_tmp[level].ensure(2 * tiles * sizeof(uint32_t)));
-    uint32_t* sums = g.scan_tmp[level].as<uint32_t>();
+    TRY(sl.scan_tmp[level].ensure(2 * tiles * sizeof(uint32_t)));
+    uint32_t* sums = sl.scan_tmp[level].as<uint32_t>();
     uint32_t* bases = sums + tiles;
     // pass 1: tile totals only (out is rewritten in pass 3)
     LAUNCH(scan_tile_kernel, (unsigned)tiles, SCAN_THREADS, 0, s, in, out, n, sums, (const uint32_t*)nullptr);
-    TRY(scan_u32(sums, bases, tiles, level + 1, s));
+    TRY(scan_u32(sl, sums, bases, tiles, level + 1, s));
     LAUNCH(scan_tile_kernel, (unsigned)tiles, SCAN_THREADS, 0, s, in, out, n, (uint32_t*)nullptr, (const uint32_t*)bases);
     return B200ZK_OK;
 }
@@ -189,16 +487,26 @@ int32_t scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, int level, cudaS
 // ------------------------------------------------------------------------------------------
 // MSM
 // ------------------------------------------------------------------------------------------
-// window bits minimising (mixed adds) + (bucket reduction); `shared` = all windows share one bucket set
+// Window bits minimising the modelled time of one MSM; `shared` = all windows share one bucket set (window tables).
+// Throughput terms: one mixed addition (~10 Fp products) per point and window, ~2.2 full additions (~31 products) per
+// bucket in the reduction tree.  Latency term: the upper levels of the tree are chains of dependent additions on a
+// nearly empty machine, one level per 4-5 bits of bucket index, which a throughput model does not see -- without it
+// small MSMs (the prover's k = 14..20 columns) get windows whose tail costs more than their accumulation.
 uint32_t msm_choose_window(uint64_t n, uint32_t batch, bool shared) {
     uint32_t best_c = 4;
     double best_cost = 1e300;
+    const double unit_rate = 2.6e10;         // Fp products per second at the ~85 % pipe utilisation of a full machine
     for (uint32_t c = 4; c <= 24; c++) {
         uint32_t W = (256 + c - 1) / c;
         double nb = (double)(1u << (c - 1));
         double sets = shared ? 1.0 : (double)W;
-        // mixed add ~10 Fp mul per point and window; bucket reduce ~2.2 full adds (14 mul) per bucket
-        double cost = W * 10.0 * (double)n + sets * 31.0 * nb;
+        double work = (W * 10.0 * (double)n + sets * 31.0 * nb) * batch / unit_rate;
+        // latency floor of the accumulation: a bucket's additions are one thread's serial chain (~7 us per addition
+        // when the machine is not full)
+        double chain = std::min(1024.0, std::max(1.0, (double)n * (shared ? W : 1) / nb)) * 7e-6;
+        double levels = (double)((c - 1 + 4) / 5);
+        double tail_latency = levels * 1.1e-4 + (shared ? 0.0 : (double)c * W * 1.2e-6);
+        double cost = std::max(work, chain) + tail_latency;
         if ((double)batch * sets * nb * 192.0 > 4.0e9 && c > 8) continue;   // bucket arrays within ~4 GB
         if (cost < best_cost) { best_cost = cost; best_c = c; }
     }
@@ -214,7 +522,7 @@ MsmPlan msm_plan(uint64_t n, uint32_t batch, const BaseTable* tab) {
         pl.row_stride = tab->n;
     } else {
         pl.c = msm_choose_window(n, batch, false);
-        if (g.tune_c >= 2 && g.tune_c <= 24) pl.c = g.tune_c;
+        if (g_tune_c >= 2 && g_tune_c <= 24) pl.c = g_tune_c;
     }
     pl.W = (256 + pl.c - 1) / pl.c;
     pl.nb = 1u << (pl.c - 1);
@@ -225,25 +533,30 @@ MsmPlan msm_plan(uint64_t n, uint32_t batch, const BaseTable* tab) {
     // further to "fill the machine" on small problems was measured to cost more in the collapse step
     // than it saved in the accumulate kernel.)
     if (smax > 1024) smax = 1024;
-    if (g.tune_smax) smax = g.tune_smax;
+    if (g_tune_smax) smax = g_tune_smax;
     pl.smax = smax;
     return pl;
 }
 
 // d_scalars: batch*n Fr (device).  d_bases: n packed Montgomery affine points.
 // One chunk of a scalar vector that arrives in pieces (host-buffer MSMs): n_total fixes the plan, i0 is the index of the
-// chunk's first point, the first chunk owns g.buckets, later chunks accumulate into g.buckets2 and are folded in, the
+// chunk's first point, the first chunk owns sl.buckets, later chunks accumulate into sl.buckets2 and are folded in, the
 // last chunk runs the tail.
 struct MsmChunk {
     uint64_t n_total, i0;
     bool first, last;
 };
-int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, uint32_t batch,
-                uint32_t scalar_fmt, uint32_t* d_out_mont, uint32_t* d_out_canon, cudaStream_t s,
-                uint32_t* d_out_xyzz = nullptr, const MsmChunk* ck = nullptr) {
-    if (n == 0 || batch == 0) {
-        if (d_out_mont) CU(cudaMemsetAsync(d_out_mont, 0, 96 * (size_t)std::max(batch, 1u), s));
-        if (d_out_canon) CU(cudaMemsetAsync(d_out_canon, 0, 96 * (size_t)std::max(batch, 1u), s));
+int32_t msm_run(Ctx& c, Slot& sl, const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, uint32_t batch,
+                uint32_t scalar_fmt, uint32_t* d_out_mont, uint32_t* d_out_canon, cudaStream_t s, uint32_t* d_out_xyzz = nullptr,
+                const MsmChunk* ck = nullptr, const XchgArgs* xa = nullptr) {
+    XchgArgs xnone{};
+    if (batch == 0) return B200ZK_OK;
+    if (n == 0) {
+        if (d_out_mont) CU(cudaMemsetAsync(d_out_mont, 0, 96 * (size_t)batch, s));
+        if (d_out_canon) CU(cudaMemsetAsync(d_out_canon, 0, 96 * (size_t)batch, s));
+        if (d_out_xyzz) CU(cudaMemsetAsync(d_out_xyzz, 0, 192 * (size_t)batch, s));
+        // an empty slice still arrives at the exchange (with the identity)
+        if (xa) LAUNCH(msm_combine_kernel, batch, 32, 0, s, (const uint32_t*)nullptr, 0u, 0u, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, *xa);
         return B200ZK_OK;
     }
     if (n >= (1ull << 31)) return fail(B200ZK_ERR_INVALID_ARG, "msm: n must be < 2^31");
@@ -255,44 +568,44 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
         return fail(B200ZK_ERR_INVALID_ARG, "msm: batch * n * windows exceeds 2^32 entries; split the batch");
     uint64_t max_tasks = std::min(NBt, max_entries) + max_entries / pl.smax + 1;
 
-    TRY(g.counts.ensure((NBt + 1) * 4));
-    TRY(g.offsets.ensure((NBt + 1) * 4));
-    TRY(g.cursor.ensure((NBt + 1) * 4));
-    TRY(g.ntask.ensure((NBt + 1) * 4));
-    TRY(g.task_off.ensure((NBt + 1) * 4));
-    TRY(g.entries.ensure(max_entries * 4));
-    TRY(g.task_bucket.ensure(max_tasks * 4));
-    TRY(g.task_start.ensure(max_tasks * 4));
-    TRY(g.task_len.ensure(max_tasks * 4));
-    TRY(g.len_hist.ensure(((size_t)pl.smax + 2) * 4));
-    TRY(g.len_off.ensure(((size_t)pl.smax + 2) * 4));
-    TRY(g.order.ensure(max_tasks * 4));
+    TRY(sl.counts.ensure((NBt + 1) * 4));
+    TRY(sl.offsets.ensure((NBt + 1) * 4));
+    TRY(sl.cursor.ensure((NBt + 1) * 4));
+    TRY(sl.ntask.ensure((NBt + 1) * 4));
+    TRY(sl.task_off.ensure((NBt + 1) * 4));
+    TRY(sl.entries.ensure(max_entries * 4));
+    TRY(sl.task_bucket.ensure(max_tasks * 4));
+    TRY(sl.task_start.ensure(max_tasks * 4));
+    TRY(sl.task_len.ensure(max_tasks * 4));
+    TRY(sl.len_hist.ensure(((size_t)pl.smax + 2) * 4));
+    TRY(sl.len_off.ensure(((size_t)pl.smax + 2) * 4));
+    TRY(sl.order.ensure(max_tasks * 4));
     const uint64_t hmax = max_entries / pl.smax + 2;                       // heavy buckets (split into > 1 task)
     const uint64_t imax = hmax + max_tasks / HEAVY_CHUNK + 2;              // their work items
-    TRY(g.heavy.ensure((4 + 3 * hmax + 2 * imax) * 4));
-    TRY(g.heavy_items.ensure(imax * 192));
-    TRY(g.buckets.ensure(NBt * 192));
-    if (ck && !ck->first) TRY(g.buckets2.ensure(NBt * 192));
-    TRY(g.partials.ensure(max_tasks * 192));
+    TRY(sl.heavy.ensure((4 + 3 * hmax + 2 * imax) * 4));
+    TRY(sl.heavy_items.ensure(imax * 192));
+    TRY(sl.buckets.ensure(NBt * 192));
+    if (ck && !ck->first) TRY(sl.buckets2.ensure(NBt * 192));
+    TRY(sl.partials.ensure(max_tasks * 192));
     uint64_t m1 = (pl.nb + RED_RADIX - 1) / RED_RADIX, m2 = (m1 + RED_RADIX - 1) / RED_RADIX;
-    TRY(g.redS[0].ensure(nwin * m1 * 192));
-    TRY(g.redA[0].ensure(nwin * m1 * 192));
-    TRY(g.redS[1].ensure(nwin * m2 * 192));
-    TRY(g.redA[1].ensure(nwin * m2 * 192));
+    TRY(sl.redS[0].ensure(nwin * m1 * 192));
+    TRY(sl.redA[0].ensure(nwin * m1 * 192));
+    TRY(sl.redS[1].ensure(nwin * m2 * 192));
+    TRY(sl.redA[1].ensure(nwin * m2 * 192));
 
-    uint32_t* counts = g.counts.as<uint32_t>();
-    uint32_t* offsets = g.offsets.as<uint32_t>();
-    uint32_t* cursor = g.cursor.as<uint32_t>();
-    uint32_t* ntask = g.ntask.as<uint32_t>();
-    uint32_t* task_off = g.task_off.as<uint32_t>();
-    uint32_t* entries = g.entries.as<uint32_t>();
-    uint32_t* buckets = (ck && !ck->first) ? g.buckets2.as<uint32_t>() : g.buckets.as<uint32_t>();
+    uint32_t* counts = sl.counts.as<uint32_t>();
+    uint32_t* offsets = sl.offsets.as<uint32_t>();
+    uint32_t* cursor = sl.cursor.as<uint32_t>();
+    uint32_t* ntask = sl.ntask.as<uint32_t>();
+    uint32_t* task_off = sl.task_off.as<uint32_t>();
+    uint32_t* entries = sl.entries.as<uint32_t>();
+    uint32_t* buckets = (ck && !ck->first) ? sl.buckets2.as<uint32_t>() : sl.buckets.as<uint32_t>();
     const uint64_t i0 = ck ? ck->i0 : 0;
-    uint32_t* partials = g.partials.as<uint32_t>();
+    uint32_t* partials = sl.partials.as<uint32_t>();
 
-    TRY(ws_enter(s));
-    g.ev_kind = 1;
-    TRY(prof_mark(0, s));
+    TRY(ws_enter(sl, s));
+    prof_select(c, sl, 1);
+    TRY(prof_mark(sl, 0, s));
     CU(cudaMemsetAsync(counts, 0, (NBt + 1) * 4, s));
     CU(cudaMemsetAsync(ntask, 0, (NBt + 1) * 4, s));
     dim3 dgrid((unsigned)((n + 255) / 256), batch);
@@ -300,17 +613,15 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     // (A two-pass sort -- coarse bins of 2048 buckets staged through shared memory, then one CTA per bin --
     // was built and measured at 2^24: 11.0 ms against 7.9 ms for this one-pass histogram + scatter; removed.)
     LAUNCH(msm_digits_kernel<0>, dgrid, 256, 0, s, d_scalars, n, fmt_mont, pl, counts, (uint32_t*)nullptr, 0u, 0xffffffffu, (const uint32_t*)nullptr, 0u, i0);
-    TRY(scan_u32(counts, offsets, NBt + 1, 0, s));
+    TRY(scan_u32(sl, counts, offsets, NBt + 1, 0, s));
     CU(cudaMemcpyAsync(cursor, offsets, (NBt + 1) * 4, cudaMemcpyDeviceToDevice, s));
     {
         // The scatter writes 4-byte entries into bucket lists that are spread over the whole entry array.  When that
         // array is much larger than L2, the 32-byte sector a list is currently filling is evicted half full and read
         // back (DRAM read-modify-write).  Scattering one bucket range at a time keeps the open sectors (32 B per bucket
         // of the range) resident; the scalars are re-read and re-coded once per pass, which is cheap.
-        static int passes_env = -1;
-        if (passes_env < 0) { const char* v = getenv("B200ZK_SCATTER_PASSES"); passes_env = v ? atoi(v) : 0; }
         uint32_t passes = 1;
-        if (passes_env > 0) passes = (uint32_t)passes_env;
+        if (g_scatter_passes_env > 0) passes = (uint32_t)g_scatter_passes_env;
         else if (NBt * 32 >= (48ull << 20)) passes = 2;   // measured at 2^24 (2^21 buckets): 1 pass 8.98 ms, 2 passes 7.44, 4 passes 9.22 (each pass re-codes every scalar)
         for (uint32_t ps = 0; ps < passes; ps++) {
             uint32_t lo = (uint32_t)(NBt * ps / passes), hi = (uint32_t)(NBt * (ps + 1) / passes);
@@ -320,12 +631,12 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     }
     unsigned bgrid = (unsigned)((NBt + 255) / 256);
     LAUNCH(msm_task_count_kernel, bgrid, 256, 0, s, (const uint32_t*)counts, NBt, pl.smax, ntask);
-    TRY(scan_u32(ntask, task_off, NBt + 1, 0, s));
-    uint32_t* len_hist = g.len_hist.as<uint32_t>();
-    uint32_t* len_off = g.len_off.as<uint32_t>();
-    uint32_t* order = g.order.as<uint32_t>();
+    TRY(scan_u32(sl, ntask, task_off, NBt + 1, 0, s));
+    uint32_t* len_hist = sl.len_hist.as<uint32_t>();
+    uint32_t* len_off = sl.len_off.as<uint32_t>();
+    uint32_t* order = sl.order.as<uint32_t>();
     HeavyArrays hv;
-    hv.count = g.heavy.as<uint32_t>();
+    hv.count = sl.heavy.as<uint32_t>();
     hv.bucket = hv.count + 4;
     hv.base = hv.bucket + hmax;
     hv.done = hv.base + hmax;
@@ -334,19 +645,19 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
     CU(cudaMemsetAsync(len_hist, 0, ((size_t)pl.smax + 2) * 4, s));
     CU(cudaMemsetAsync(hv.count, 0, 16, s));
     LAUNCH(msm_task_emit_kernel, bgrid, 256, 0, s, (const uint32_t*)counts, (const uint32_t*)offsets,
-           (const uint32_t*)task_off, NBt, pl.smax, g.task_bucket.as<uint32_t>(), g.task_start.as<uint32_t>(),
-           g.task_len.as<uint32_t>(), len_hist);
-    TRY(scan_u32(len_hist, len_off, (uint64_t)pl.smax + 1, 0, s));
-    LAUNCH(msm_task_order_kernel, (unsigned)((max_tasks + 255) / 256), 256, 0, s, (const uint32_t*)g.task_len.as<uint32_t>(),
+           (const uint32_t*)task_off, NBt, pl.smax, sl.task_bucket.as<uint32_t>(), sl.task_start.as<uint32_t>(),
+           sl.task_len.as<uint32_t>(), len_hist);
+    TRY(scan_u32(sl, len_hist, len_off, (uint64_t)pl.smax + 1, 0, s));
+    LAUNCH(msm_task_order_kernel, (unsigned)((max_tasks + 255) / 256), 256, 0, s, (const uint32_t*)sl.task_len.as<uint32_t>(),
            (const uint32_t*)(task_off + NBt), pl.smax, len_off, order);
     LAUNCH(msm_heavy_list_kernel, bgrid, 256, 0, s, (const uint32_t*)ntask, NBt, hv);
     CU(cudaMemsetAsync(buckets, 0, NBt * 192, s));
-    TRY(prof_mark(1, s));
+    TRY(prof_mark(sl, 1, s));
     {
         unsigned agrid = (unsigned)((max_tasks + 127) / 128);
-        const uint32_t *tb = g.task_bucket.as<uint32_t>(), *ts = g.task_start.as<uint32_t>(), *tl = g.task_len.as<uint32_t>();
+        const uint32_t *tb = sl.task_bucket.as<uint32_t>(), *ts = sl.task_start.as<uint32_t>(), *tl = sl.task_len.as<uint32_t>();
         const uint32_t* ntp = task_off + NBt;
-        switch (g.tune_variant) {
+        switch (g_tune_variant) {
             case 1: LAUNCH(msm_accumulate_kernel_v1, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
             case 2: LAUNCH(msm_accumulate_kernel_v2, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
             case 7: LAUNCH(msm_accumulate_kernel_v7, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
@@ -355,32 +666,32 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
             case 4:
             case 5: {
                 size_t slots = max_entries / 2 + 2;
-                TRY(g.aff_a.ensure(slots * 96));
-                TRY(g.aff_b.ensure(slots * 96));
-                TRY(g.aff_pre.ensure(slots * 48));
-                if (g.tune_variant == 4)
+                TRY(sl.aff_a.ensure(slots * 96));
+                TRY(sl.aff_b.ensure(slots * 96));
+                TRY(sl.aff_pre.ensure(slots * 48));
+                if (g_tune_variant == 4)
                     LAUNCH(msm_accumulate_affine_kernel, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials,
-                           g.aff_a.as<uint32_t>(), g.aff_b.as<uint32_t>(), g.aff_pre.as<uint32_t>());
+                           sl.aff_a.as<uint32_t>(), sl.aff_b.as<uint32_t>(), sl.aff_pre.as<uint32_t>());
                 else
                     LAUNCH(msm_accumulate_affine_kernel_r168, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials,
-                           g.aff_a.as<uint32_t>(), g.aff_b.as<uint32_t>(), g.aff_pre.as<uint32_t>());
+                           sl.aff_a.as<uint32_t>(), sl.aff_b.as<uint32_t>(), sl.aff_pre.as<uint32_t>());
                 break;
             }
             default: LAUNCH(msm_accumulate_kernel, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
         }
     }
-    TRY(prof_mark(2, s));
-    LAUNCH(msm_collapse_kernel, (unsigned)(g.prop.multiProcessorCount * 4), 128, 0, s, (const uint32_t*)ntask,
-           (const uint32_t*)task_off, hv, (const uint32_t*)partials, g.heavy_items.as<uint32_t>(), buckets);
+    TRY(prof_mark(sl, 2, s));
+    LAUNCH(msm_collapse_kernel, (unsigned)(c.prop.multiProcessorCount * 4), 128, 0, s, (const uint32_t*)ntask,
+           (const uint32_t*)task_off, hv, (const uint32_t*)partials, sl.heavy_items.as<uint32_t>(), buckets);
 
     if (ck && !ck->first)
-        LAUNCH(msm_bucket_merge_kernel, (unsigned)((NBt + 127) / 128), 128, 0, s, g.buckets.as<uint32_t>(), (const uint32_t*)buckets, NBt);
+        LAUNCH(msm_bucket_merge_kernel, (unsigned)((NBt + 127) / 128), 128, 0, s, sl.buckets.as<uint32_t>(), (const uint32_t*)buckets, NBt);
     if (ck && !ck->last) {
-        TRY(ws_leave(s));
-        g.last_plan = pl;
+        TRY(ws_leave(sl, s));
+        sl.last_plan = pl;
         return B200ZK_OK;
     }
-    buckets = g.buckets.as<uint32_t>();
+    buckets = sl.buckets.as<uint32_t>();
 
     // bucket reduction tree: work-efficient serial radix-16 groups while there are enough of them to fill
     // the machine, then warp-cooperative radix-32 groups (short dependency chains) for the upper levels
@@ -395,8 +706,8 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
         bool serial = (uint64_t)((m + RED_RADIX - 1) / RED_RADIX) * nwin >= 4096;
         uint32_t radix = serial ? RED_RADIX : COOP_RADIX;
         uint32_t m_out = (m + radix - 1) / radix;
-        uint32_t* S_out = g.redS[pp].as<uint32_t>();
-        uint32_t* A_out = g.redA[pp].as<uint32_t>();
+        uint32_t* S_out = sl.redS[pp].as<uint32_t>();
+        uint32_t* A_out = sl.redA[pp].as<uint32_t>();
         uint64_t groups = (uint64_t)m_out * nwin;
         if (serial)
             LAUNCH(msm_reduce_kernel, (unsigned)((groups + 63) / 64), 64, 0, s, S_in, A_in, S_out, A_out, m, m_out,
@@ -414,30 +725,39 @@ int32_t msm_run(const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d
         scale_log += serial ? RED_LOG : COOP_LOG;
         pp ^= 1;
     } while (m > 1);
-    LAUNCH(msm_combine_kernel, batch, 32, 0, s, win_sums, pl.precomp ? 1u : pl.W, pl.c, d_out_mont, d_out_canon, d_out_xyzz);
-    TRY(prof_mark(3, s));
-    TRY(ws_leave(s));
-    g.last_plan = pl;
+    LAUNCH(msm_combine_kernel, batch, 32, 0, s, win_sums, pl.precomp ? 1u : pl.W, pl.c, d_out_mont, d_out_canon, d_out_xyzz, xa ? *xa : xnone);
+    TRY(prof_mark(sl, 3, s));
+    TRY(ws_leave(sl, s));
+    sl.last_plan = pl;
     return B200ZK_OK;
 }
 
-int32_t lookup_bases(uint64_t handle, uint64_t offset, uint64_t n, const uint32_t** out, const BaseTable** tab = nullptr) {
-    auto it = g.tables.find(handle);
-    if (it == g.tables.end()) return fail(B200ZK_ERR_BAD_HANDLE, "unknown base-table handle");
-    if (offset > it->second.n || n > it->second.n - offset)
-        return fail(B200ZK_ERR_INVALID_ARG, "msm: offset + n exceeds the registered table");
-    *out = it->second.d + 24 * offset;
-    if (tab) *tab = &it->second;
+std::shared_ptr<TableSet> find_table(uint64_t handle) {
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    auto it = g_tables.find(handle);
+    return it == g_tables.end() ? nullptr : it->second;
+}
+int32_t get_table(uint64_t handle, uint64_t offset, uint64_t n, std::shared_ptr<TableSet>* out) {
+    auto ts = find_table(handle);
+    if (!ts) return fail(B200ZK_ERR_BAD_HANDLE, "unknown base-table handle");
+    if (offset > ts->n || n > ts->n - offset) return fail(B200ZK_ERR_INVALID_ARG, "msm: offset + n exceeds the registered table");
+    *out = ts;
     return B200ZK_OK;
 }
+// the shard of `ts` on device `dev` that holds all of [offset, offset + n), or null
+const TableShard* shard_on(const TableSet& ts, int dev, uint64_t offset, uint64_t n) {
+    for (const TableShard& sh : ts.shards)
+        if (sh.dev == dev && offset >= sh.start && offset + n <= sh.start + sh.n) return &sh;
+    return nullptr;
+}
 
-int32_t ingest_bases(const uint8_t* d_src, uint64_t n, uint32_t fmt, uint32_t stride, uint32_t* d_dst, cudaStream_t s) {
-    TRY(g.flag.ensure(4));
-    CU(cudaMemsetAsync(g.flag.p, 0, 4, s));
+int32_t ingest_bases(Ctx& c, const uint8_t* d_src, uint64_t n, uint32_t fmt, uint32_t stride, uint32_t* d_dst, cudaStream_t s) {
+    TRY(c.reg_flag.ensure(4));
+    CU(cudaMemsetAsync(c.reg_flag.p, 0, 4, s));
     LAUNCH(g1_ingest_kernel, (unsigned)((n + 127) / 128), 128, 0, s, d_src, n, stride, fmt == B200ZK_FMT_MONT ? 1u : 0u,
-           d_dst, g.flag.as<uint32_t>());
+           d_dst, c.reg_flag.as<uint32_t>());
     uint32_t bad = 0;
-    CU(cudaMemcpyAsync(&bad, g.flag.p, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&bad, c.reg_flag.p, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     if (bad) return fail(B200ZK_ERR_BAD_POINT, "a base point is not a canonical point on the curve");
     return B200ZK_OK;
@@ -452,13 +772,16 @@ int32_t upload_fr_mont(const uint8_t v[32], uint32_t* d_dst, cudaStream_t s) {
     return B200ZK_OK;
 }
 
-int32_t ntt_get_plan(uint32_t log_n, const uint8_t omega[32], bool inverse, cudaStream_t s, NttPlan** out) {
+// plans and coset tables are per device and built once (under the device mutex, on the utility stream)
+int32_t ntt_get_plan(Ctx& c, uint32_t log_n, const uint8_t omega[32], bool inverse, NttPlan** out) {
+    std::lock_guard<std::mutex> lk(c.mu);
     NttKey key;
     key.log_n = log_n;
     key.inverse = inverse ? 1 : 0;
     memcpy(key.omega, omega, 32);
-    auto it = g.ntt_plans.find(key);
-    if (it != g.ntt_plans.end()) { *out = &it->second; return B200ZK_OK; }
+    auto it = c.ntt_plans.find(key);
+    if (it != c.ntt_plans.end()) { *out = &it->second; return B200ZK_OK; }
+    cudaStream_t s = c.stream;
     NttPlan pl;
     pl.log_n = log_n;
     pl.npass = (log_n + NTT_LOGB - 1) / NTT_LOGB;
@@ -490,17 +813,19 @@ int32_t ntt_get_plan(uint32_t log_n, const uint8_t omega[32], bool inverse, cuda
     }
     CU(cudaStreamSynchronize(s));
     CU(cudaFree(d_omega));
-    auto ins = g.ntt_plans.emplace(key, pl);
+    auto ins = c.ntt_plans.emplace(key, pl);
     *out = &ins.first->second;
     return B200ZK_OK;
 }
 
-int32_t ntt_get_coset(uint32_t log_n, const uint8_t shift[32], cudaStream_t s, uint32_t** out) {
+int32_t ntt_get_coset(Ctx& c, uint32_t log_n, const uint8_t shift[32], uint32_t** out) {
+    std::lock_guard<std::mutex> lk(c.mu);
     CosetKey key;
     key.log_n = log_n;
     memcpy(key.shift, shift, 32);
-    auto it = g.coset_tables.find(key);
-    if (it != g.coset_tables.end()) { *out = it->second; return B200ZK_OK; }
+    auto it = c.coset_tables.find(key);
+    if (it != c.coset_tables.end()) { *out = it->second; return B200ZK_OK; }
+    cudaStream_t s = c.stream;
     uint64_t n = (uint64_t)1 << log_n;
     uint32_t *d_shift = nullptr, *tab = nullptr;
     CU(cudaMalloc(&d_shift, 32));
@@ -510,51 +835,59 @@ int32_t ntt_get_coset(uint32_t log_n, const uint8_t shift[32], cudaStream_t s, u
            (uint64_t)1, 0u, 0u);
     CU(cudaStreamSynchronize(s));
     CU(cudaFree(d_shift));
-    g.coset_tables[key] = tab;
+    c.coset_tables[key] = tab;
     *out = tab;
     return B200ZK_OK;
 }
 
-int32_t ntt_run(uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
-                const uint8_t* coset_shift, cudaStream_t s) {
+int32_t ntt_set_attrs(Ctx& c) {
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.ntt_attr_set) return B200ZK_OK;
+    CU(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+    CU(cudaFuncSetAttribute(ntt_pass_kernel_occ2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+    CU(cudaFuncSetAttribute(ntt_pass_kernel_call2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+    CU(cudaFuncSetAttribute(ntt_pass_kernel_call3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+    CU(cudaFuncSetAttribute(ntt_pass_kernel_plain2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+    CU(cudaFuncSetAttribute(ntt_pass_kernel_wl2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+    c.ntt_attr_set = true;
+    return B200ZK_OK;
+}
+
+int32_t ntt_check_args(uint32_t log_n, uint32_t flags, const uint8_t* coset_shift) {
     if (log_n > 32) return fail(B200ZK_ERR_INVALID_ARG, "ntt: log_n exceeds the 2-adicity of Fr");
     if ((flags & (B200ZK_NTT_COSET_IN | B200ZK_NTT_COSET_OUT)) && !coset_shift)
         return fail(B200ZK_ERR_INVALID_ARG, "ntt: COSET flag without a shift");
     if ((flags & B200ZK_NTT_COSET_IN) && (flags & B200ZK_NTT_COSET_OUT))
         return fail(B200ZK_ERR_INVALID_ARG, "ntt: COSET_IN and COSET_OUT are mutually exclusive");
+    return B200ZK_OK;
+}
+
+int32_t ntt_run(Ctx& c, Slot& sl, uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
+                const uint8_t* coset_shift, cudaStream_t s) {
+    TRY(ntt_check_args(log_n, flags, coset_shift));
     if (batch == 0) return B200ZK_OK;
     bool inverse = (flags & B200ZK_NTT_INVERSE_SCALE) != 0;
     NttPlan* pl = nullptr;
-    TRY(ntt_get_plan(log_n, omega, inverse, s, &pl));
+    TRY(ntt_get_plan(c, log_n, omega, inverse, &pl));
     uint32_t* coset = nullptr;
-    if (flags & (B200ZK_NTT_COSET_IN | B200ZK_NTT_COSET_OUT)) TRY(ntt_get_coset(log_n, coset_shift, s, &coset));
+    if (flags & (B200ZK_NTT_COSET_IN | B200ZK_NTT_COSET_OUT)) TRY(ntt_get_coset(c, log_n, coset_shift, &coset));
     uint64_t n = (uint64_t)1 << log_n, total = n * batch;
     uint32_t* bufs[2] = {nullptr, nullptr};
     if (pl->npass > 1) {
-        TRY(g.ntt_tmp[0].ensure(total * 32));
-        bufs[0] = g.ntt_tmp[0].as<uint32_t>();
+        TRY(sl.ntt_tmp[0].ensure(total * 32));
+        bufs[0] = sl.ntt_tmp[0].as<uint32_t>();
         if (pl->npass > 2) {
-            TRY(g.ntt_tmp[1].ensure(total * 32));
-            bufs[1] = g.ntt_tmp[1].as<uint32_t>();
+            TRY(sl.ntt_tmp[1].ensure(total * 32));
+            bufs[1] = sl.ntt_tmp[1].as<uint32_t>();
         }
     }
-    static bool attr_set = false;
-    static int ntt_variant = 1;   // 1: two CTAs per SM (default); 0: one CTA per SM.  B200ZK_NTT_VARIANT overrides.
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
-        CU(cudaFuncSetAttribute(ntt_pass_kernel_occ2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
-        CU(cudaFuncSetAttribute(ntt_pass_kernel_call2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
-        CU(cudaFuncSetAttribute(ntt_pass_kernel_call3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
-        CU(cudaFuncSetAttribute(ntt_pass_kernel_plain2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
-        CU(cudaFuncSetAttribute(ntt_pass_kernel_wl2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
-        if (const char* v = getenv("B200ZK_NTT_VARIANT")) ntt_variant = atoi(v);
-        attr_set = true;
-    }
+    TRY(ntt_set_attrs(c));
+    const int ntt_variant = g_ntt_variant;
     uint32_t log_s = 0;
     const uint32_t* src = d_data;
-    TRY(ws_enter(s));
-    g.ev_kind = 2;
-    TRY(prof_mark(0, s));
+    TRY(ws_enter(sl, s));
+    prof_select(c, sl, 2);
+    TRY(prof_mark(sl, 0, s));
     for (uint32_t i = 0; i < pl->npass; i++) {
         bool last = (i + 1 == pl->npass);
         uint32_t* dst = last ? d_data : bufs[i & 1];
@@ -581,207 +914,12 @@ int32_t ntt_run(uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t 
         else if (ntt_variant == 4) LAUNCH(ntt_pass_kernel_plain2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         else if (ntt_variant == 5) LAUNCH(ntt_pass_kernel_wl2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         else LAUNCH(ntt_pass_kernel_occ2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
-        TRY(prof_mark((int)i + 1, s));
+        TRY(prof_mark(sl, (int)i + 1, s));
         src = dst;
         log_s += pl->deg[i];
     }
-    TRY(ws_leave(s));
+    TRY(ws_leave(sl, s));
     return B200ZK_OK;
-}
-
-// ------------------------------------------------------------------------------------------
-// self-test and micro-benchmark kernels
-// ------------------------------------------------------------------------------------------
-template <class P>
-__global__ void selftest_kernel(const uint32_t* a, const uint32_t* b, uint32_t* out, uint64_t count, uint32_t op) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    Fe<P> x, y, r;
-    for (int k = 0; k < P::N; k++) { x.l[k] = a[P::N * i + k]; y.l[k] = b ? b[P::N * i + k] : 0; }
-    x = fe_to_mont(x);
-    y = fe_to_mont(y);
-    if (op == 0) r = fe_mul(x, y);
-    else if (op == 1) r = fe_add(x, y);
-    else if (op == 2) r = fe_sub(x, y);
-    else r = fe_inv(x);
-    r = fe_from_mont(r);
-    for (int k = 0; k < P::N; k++) out[P::N * i + k] = r.l[k];
-}
-
-__global__ void __launch_bounds__(256) mb_imad_wide_kernel(uint64_t* out, uint32_t iters, uint32_t a0, uint32_t b0) {
-    // plain IMAD.WIDE.U32 (no carry in or out); the multiplicand rotates through the other
-    // accumulators so that ptxas cannot hoist the product out of the loop
-    uint64_t acc[8];
-    uint32_t b = b0 + blockIdx.x;
-#pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = a0 + threadIdx.x * 8 + k;
-    for (uint32_t it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) acc[k] = (uint64_t)(uint32_t)acc[(k + 1) & 7] * b + acc[k];
-        }
-    }
-    uint64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) s ^= acc[k];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-__global__ void __launch_bounds__(256) mb_imad_pair_kernel(uint64_t* out, uint32_t iters, uint32_t a0, uint32_t b0) {
-    uint32_t lo[8], hi[8];
-    uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
-#pragma unroll
-    for (int k = 0; k < 8; k++) { lo[k] = k; hi[k] = k + 1; }
-    for (uint32_t it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[k]) : "r"(a), "r"(b));
-                asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(hi[k]) : "r"(a), "r"(b));
-            }
-        }
-    }
-    uint64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) s ^= ((uint64_t)hi[k] << 32) | lo[k];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-// carry-chained rows exactly as fe_mul issues them: 4 independent rows of 6 IMAD.WIDE.U32.X
-__global__ void __launch_bounds__(256) mb_imad_chain_kernel(uint64_t* out, uint32_t iters, uint32_t a0, uint32_t b0) {
-    uint32_t acc[4][12];
-    uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int k = 0; k < 12; k++) acc[r][k] = r * 12 + k;
-    for (uint32_t it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            mad_wide_cc(acc[r][0], acc[r][1], a, b, acc[r][0], acc[r][1]);
-#pragma unroll
-            for (int k = 2; k < 12; k += 2) madc_wide_cc(acc[r][k], acc[r][k + 1], a, b, acc[r][k], acc[r][k + 1]);
-        }
-    }
-    uint64_t s = 0;
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int k = 0; k < 12; k++) s = s * 31 + acc[r][k];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-// every wide MAD produces a carry-out but takes no carry-in
-__global__ void __launch_bounds__(256) mb_imad_cout_kernel(uint64_t* out, uint32_t iters, uint32_t a0, uint32_t b0) {
-    uint32_t lo[8], hi[8];
-    uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
-#pragma unroll
-    for (int k = 0; k < 8; k++) { lo[k] = k; hi[k] = k + 1; }
-    uint32_t sink = 0;
-    for (uint32_t it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) mad_wide_cc(lo[k], hi[k], a, b, lo[k], hi[k]);
-        }
-        sink = addc(sink, 0);
-    }
-    uint64_t s = sink;
-#pragma unroll
-    for (int k = 0; k < 8; k++) s ^= ((uint64_t)hi[k] << 32) | lo[k];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-__global__ void __launch_bounds__(256) mb_dfma_kernel(uint64_t* out, uint32_t iters, double a0, double b0) {
-    double acc[8];
-    double a = a0 + threadIdx.x * 1e-9, b = b0 + blockIdx.x * 1e-9;
-#pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = k;
-    for (uint32_t it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc[k]) : "d"(a), "d"(b));
-        }
-    }
-    double s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) s += acc[k];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = (uint64_t)__double_as_longlong(s);
-}
-// one LOP3 (ALU pipe) per IMAD.WIDE (FMA pipe): do the two pipes issue side by side?
-__global__ void __launch_bounds__(256) mb_imad_alu_kernel(uint64_t* out, uint32_t iters, uint32_t a0, uint32_t b0) {
-    uint64_t acc[8];
-    uint32_t x[8];
-    uint32_t b = b0 + blockIdx.x;
-#pragma unroll
-    for (int k = 0; k < 8; k++) { acc[k] = a0 + threadIdx.x * 8 + k; x[k] = k * 3; }
-    for (uint32_t it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                acc[k] = (uint64_t)(uint32_t)acc[(k + 1) & 7] * b + acc[k];
-                x[k] = (x[k] ^ x[(k + 3) & 7]) & ~x[(k + 5) & 7];
-            }
-        }
-    }
-    uint64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) s ^= acc[k] + x[k];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-// MODE 0: IMAD.HI.U32 only; 1: 32-bit IMAD only; 2: unfused pair IMAD + IMAD.HI.U32 on the same operands with an
-// immediate multiplier (what ptxas emits for the m*p rows when the modulus limb is not in a plain register).
-// The multiplicand rotates through the accumulators so that nothing can be hoisted.
-template <int MODE>
-__global__ void __launch_bounds__(256) mb_imad_parts_kernel(uint64_t* out, uint32_t iters, uint32_t a0, uint32_t b0) {
-    uint32_t lo[8], hi[8];
-    uint32_t b = b0 + blockIdx.x;
-#pragma unroll
-    for (int k = 0; k < 8; k++) { lo[k] = a0 + threadIdx.x * 8 + k; hi[k] = k + 1; }
-    for (uint32_t it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (MODE == 0) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(hi[k]) : "r"(hi[(k + 1) & 7]), "r"(b));
-                else if (MODE == 1) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[k]) : "r"(lo[(k + 1) & 7]), "r"(b));
-                else {
-                    uint32_t m = lo[(k + 1) & 7];
-                    asm volatile("mad.lo.cc.u32 %0, %2, 0x53bda402, %0;\n\tmadc.hi.u32 %1, %2, 0x53bda402, %1;"
-                                 : "+r"(lo[k]), "+r"(hi[k]) : "r"(m));
-                }
-            }
-        }
-    }
-    uint64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) s ^= ((uint64_t)hi[k] << 32) | lo[k];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-template <class P>
-__global__ void __launch_bounds__(256) mb_femul_kernel(uint32_t* out, uint32_t iters) {
-    Fe<P> x = fe_one<P>(), y = fe_one<P>();
-    x.l[0] += threadIdx.x;
-    y.l[1] += blockIdx.x;
-    for (uint32_t it = 0; it < iters; it++) {
-        x = fe_mul(x, y);
-        y = fe_mul(y, x);
-    }
-    uint32_t s = 0;
-    for (int k = 0; k < P::N; k++) s ^= x.l[k] ^ y.l[k];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-__global__ void __launch_bounds__(128) mb_madd_kernel(const uint32_t* gen_mont, uint32_t* out, uint32_t iters) {
-    G1Affine q = g1a_ldg(gen_mont, 0);
-    G1Xyzz acc;
-    xyzz_from_affine(acc, q, false);
-    xyzz_dbl(acc);
-    for (uint32_t k = 0; k < (threadIdx.x & 7); k++) xyzz_dbl(acc);
-    for (uint32_t it = 0; it < iters; it++) xyzz_add_mixed(acc, q, false);
-    uint32_t s = 0;
-    for (int k = 0; k < 12; k++) s ^= acc.x.l[k] ^ acc.zzz.l[k];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 // generator of G1 in canonical wire form (its compressed form is the KAT at
@@ -793,49 +931,457 @@ const uint8_t G1_GEN_Y_BE[48] = {0x08, 0xb3, 0xf4, 0x81, 0xe3, 0xaa, 0xa0, 0xf1,
                                  0xfc, 0xf5, 0xe0, 0x95, 0xd5, 0xd0, 0x0a, 0xf6, 0x00, 0xdb, 0x18, 0xcb, 0x2c, 0x04, 0xb3, 0xed,
                                  0xd0, 0x3c, 0xc7, 0x44, 0xa2, 0x88, 0x8a, 0xe4, 0x0c, 0xaa, 0x23, 0x29, 0x46, 0xc5, 0xe7, 0xe1};
 
-// device copy of the generator (Montgomery affine), built on first use
-int32_t get_generator_dev(uint32_t** out, cudaStream_t s) {
-    static uint32_t* d_gen = nullptr;
-    if (!d_gen) {
+// the device's copy of the generator (Montgomery affine), built on first use.  Guarded by its own mutex and using its own
+// scratch: entry points of the other translation units call this while they hold the device mutex.
+int32_t get_generator_dev(Ctx& c, uint32_t** out, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(c.gen_mu);
+    if (!c.d_gen) {
         uint8_t wire[96];
         for (int i = 0; i < 48; i++) { wire[i] = G1_GEN_X_BE[47 - i]; wire[48 + i] = G1_GEN_Y_BE[47 - i]; }
         uint8_t* d_wire = nullptr;
-        CU(cudaMalloc(&d_wire, 96));
-        CU(cudaMalloc(&d_gen, 96));
+        uint32_t* d_flag = nullptr;
+        CU(cudaMalloc(&d_wire, 96 + 16));
+        CU(cudaMalloc(&c.d_gen, 96));
+        d_flag = reinterpret_cast<uint32_t*>(d_wire + 96);
         CU(cudaMemcpyAsync(d_wire, wire, 96, cudaMemcpyHostToDevice, s));
-        int32_t rc = ingest_bases(d_wire, 1, B200ZK_FMT_CANONICAL, 96, d_gen, s);
+        CU(cudaMemsetAsync(d_flag, 0, 4, s));
+        LAUNCH(g1_ingest_kernel, 1, 128, 0, s, (const uint8_t*)d_wire, (uint64_t)1, 96u, 0u, c.d_gen, d_flag);
+        CU(cudaStreamSynchronize(s));
         cudaFree(d_wire);
-        if (rc != B200ZK_OK) { cudaFree(d_gen); d_gen = nullptr; return rc; }
     }
-    *out = d_gen;
+    *out = c.d_gen;
     return B200ZK_OK;
 }
 
-}  // namespace
+// ------------------------------------------------------------------------------------------
+// host-buffer MSM on one device
+// ------------------------------------------------------------------------------------------
+// where the scalar columns of a call live on the host: an array of pointers (separate Vecs) or one block
+struct ColSrc {
+    const uint8_t* const* ptrs = nullptr;
+    const uint8_t* base = nullptr;
+    size_t stride = 0;   // bytes between consecutive columns of `base`
+    // resident scalars of a sharded call: slice k lives in the HBM of the GPU that holds shard k of the table (one column)
+    const void* const* dev_slices = nullptr;
+    const uint8_t* col(uint32_t j) const { return ptrs ? ptrs[j] : base + (size_t)j * stride; }
+};
 
-// what b200zk_ext.cu shares with this context (ctx.hpp)
-namespace b200zk_ctx {
-int32_t fail(int32_t code, const std::string& msg) { return ::fail(code, msg); }
-std::mutex& mutex() { return g_mu; }
-int32_t need_init() { return ::need_init(); }
-cudaStream_t stream() { return g.stream; }
-int sm_count() { return g.prop.multiProcessorCount; }
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-int32_t generator_dev(uint32_t** out, cudaStream_t s) { return get_generator_dev(out, s); }
-static std::vector<void (*)()> g_hooks;
-void on_shutdown(void (*fn)()) { g_hooks.push_back(fn); }
-int32_t ws_enter(cudaStream_t s) { return ::ws_enter(s); }
-int32_t ws_leave(cudaStream_t s) { return ::ws_leave(s); }
-}  // namespace b200zk_ctx
+// copies scalars [i0, i0 + n) of columns [col0, col0 + ncols) to d_dst (column-major, n per column)
+int32_t upload_columns(const ColSrc& src, uint32_t col0, uint32_t ncols, uint64_t i0, uint64_t n, uint8_t* d_dst, cudaStream_t s) {
+    const size_t colb = (size_t)n * 32;
+    if (!src.ptrs && src.stride == colb) {
+        CU(cudaMemcpyAsync(d_dst, src.base + (size_t)col0 * src.stride + i0 * 32, colb * ncols, cudaMemcpyHostToDevice, s));
+        return B200ZK_OK;
+    }
+    for (uint32_t j = 0; j < ncols; j++)
+        CU(cudaMemcpyAsync(d_dst + (size_t)j * colb, src.col(col0 + j) + i0 * 32, colb, cudaMemcpyHostToDevice, s));
+    return B200ZK_OK;
+}
 
-// ==========================================================================================
-// C ABI
-// ==========================================================================================
-extern "C" {
+// Columns [col0, col0 + ncols) of a call, points [i0, i0 + n) of each, against tab (whose point 0 pairs with scalar
+// index i0 when bases_off is the matching offset).  Either writes the finished commitments to `out` (96 bytes per
+// column) or, with an exchange, leaves its XYZZ partials at the meeting point.  Enqueues on the slot's stream and
+// waits for it.
+int32_t msm_host_device(Ctx& c, Slot& sl, const BaseTable* tab, uint64_t bases_off, const ColSrc& src, uint32_t col0, uint32_t ncols,
+                        uint64_t i0, uint64_t n, uint32_t scalar_fmt, const XchgArea* area, uint8_t* out) {
+    cudaStream_t s = sl.stream;
+    const uint32_t* d_bases = tab->d + 24 * bases_off;
+    const size_t bytes = (size_t)n * ncols * 32;
+    if (src.dev_slices) {
+        // scalars already in this GPU's HBM: straight to the kernels, the partial goes to the meeting point
+        XchgArgs xa = area->args(0);
+        TRY(msm_run(c, sl, tab, d_bases, reinterpret_cast<const uint32_t*>(src.dev_slices[area->part]), n, 1, scalar_fmt, nullptr, nullptr, s,
+                    nullptr, nullptr, &xa));
+        CU(cudaStreamSynchronize(s));
+        return B200ZK_OK;
+    }
+    TRY(sl.scalars.ensure(bytes + 16));
+    TRY(sl.out_canon.ensure((size_t)ncols * 96));
+    TRY(sl.h_out.ensure((size_t)ncols * 96 + 16));
+    uint8_t* d_sc = sl.scalars.as<uint8_t>();
+    uint32_t* d_out = area ? nullptr : sl.out_canon.as<uint32_t>();
+    {
+        const uint32_t gcols = ncols;                          // (an exchange has at most XCHG_MAX_COLS columns: checked by the caller)
+        XchgArgs xa{};
+        if (area) xa = area->args(0);
+        const XchgArgs* xp = area ? &xa : nullptr;
+        uint32_t* d_sc32 = reinterpret_cast<uint32_t*>(d_sc);
+        uint64_t nA = 0;
+        if (gcols == 1 && g_chunk_min > 0 && n >= (uint64_t)g_chunk_min) {
+            // first piece = 1/8 of the points: its copy (1.2 ms at 2^24) is the only exposed transfer, and its sort + accumulate
+            // (9 ms) cover the copy of the other 7/8 (8.5 ms).  Measured at 2^24: 84.9 ms unchunked, 83.1 ms with halves.
+            // From pageable memory (a plain Rust Vec) the copy runs at ~11 GB/s instead of ~55: the balance point
+            // copy(rest) = compute(first) moves from 1/8 to 3/8 (measured at 2^24, pageable: 122.8 ms unchunked, 118.7 with 1/8).
+            cudaPointerAttributes pa{};
+            bool pinned = cudaPointerGetAttributes(&pa, src.col(col0)) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+            cudaGetLastError();
+            nA = ((pinned ? n / 8 : 3 * (n / 8)) + 255) & ~(uint64_t)255;
+            if (nA >= n) nA = 0;                               // (tiny n with a lowered threshold: no chunking)
+        }
+        if (nA) {
+            // The second piece of the scalars crosses PCIe while the first is sorted and accumulated: the first piece's
+            // buckets are sl.buckets, the second accumulates into sl.buckets2 and is folded in before the tail.
+            // (the first piece's kernels are enqueued before the second copy is issued: from pageable host memory a copy
+            // blocks the calling thread, and the device must already have work by then)
+            TRY(slot_streams(sl));
+            const uint64_t nB = n - nA;
+            const uint8_t* h = src.col(col0) + i0 * 32;
+            MsmChunk ca{n, 0, true, false}, cb{n, nA, false, true};
+            CU(cudaMemcpyAsync(d_sc32, h, nA * 32, cudaMemcpyHostToDevice, sl.copy_stream));
+            CU(cudaEventRecord(sl.copy_ev[0], sl.copy_stream));
+            CU(cudaStreamWaitEvent(s, sl.copy_ev[0], 0));
+            TRY(msm_run(c, sl, tab, d_bases, d_sc32, nA, 1, scalar_fmt, nullptr, nullptr, s, nullptr, &ca));
+            CU(cudaMemcpyAsync(d_sc32 + 8 * nA, h + nA * 32, nB * 32, cudaMemcpyHostToDevice, sl.copy_stream));
+            CU(cudaEventRecord(sl.copy_ev[1], sl.copy_stream));
+            CU(cudaStreamWaitEvent(s, sl.copy_ev[1], 0));
+            TRY(msm_run(c, sl, tab, d_bases, d_sc32 + 8 * nA, nB, 1, scalar_fmt, nullptr, d_out, s, nullptr, &cb, xp));
+        } else if (gcols >= 4 && g_chunk_min > 0 && bytes >= g_batch_stream_min) {
+            // The prover's pattern (all columns of a phase in one call): the columns are independent, so the first eighth of
+            // them goes up and starts computing while the others cross PCIe; no merge is needed.
+            TRY(slot_streams(sl));
+            const uint32_t bA = std::max(1u, gcols / 8), bB = gcols - bA;
+            XchgArgs xb = xa;
+            xb.col0 = bA;
+            TRY(upload_columns(src, col0, bA, i0, n, reinterpret_cast<uint8_t*>(d_sc32), sl.copy_stream));
+            CU(cudaEventRecord(sl.copy_ev[0], sl.copy_stream));
+            CU(cudaStreamWaitEvent(s, sl.copy_ev[0], 0));
+            TRY(msm_run(c, sl, tab, d_bases, d_sc32, n, bA, scalar_fmt, nullptr, d_out, s, nullptr, nullptr, xp));
+            TRY(upload_columns(src, col0 + bA, bB, i0, n, reinterpret_cast<uint8_t*>(d_sc32 + 8 * (size_t)n * bA), sl.copy_stream));
+            CU(cudaEventRecord(sl.copy_ev[1], sl.copy_stream));
+            CU(cudaStreamWaitEvent(s, sl.copy_ev[1], 0));
+            TRY(msm_run(c, sl, tab, d_bases, d_sc32 + 8 * (size_t)n * bA, n, bB, scalar_fmt, nullptr, d_out ? d_out + 24 * (size_t)bA : nullptr,
+                        s, nullptr, nullptr, area ? &xb : nullptr));
+        } else {
+            TRY(upload_columns(src, col0, gcols, i0, n, reinterpret_cast<uint8_t*>(d_sc32), s));
+            TRY(msm_run(c, sl, tab, d_bases, d_sc32, n, gcols, scalar_fmt, nullptr, d_out, s, nullptr, nullptr, xp));
+        }
+    }
+    const bool readback = !area || area->fetch;
+    if (area && area->fetch) {
+        XchgArgs xa = area->args(0);
+        TRY(sl.flag.ensure(4));
+        CU(cudaMemsetAsync(sl.flag.p, 0, 4, s));
+        LAUNCH(xchg_fetch_kernel, ncols, 32, 0, s, (const unsigned long long*)xa.done, xa.seq, (const uint32_t*)xa.res_mont,
+               (const uint32_t*)xa.res_canon, (uint32_t*)nullptr, sl.out_canon.as<uint32_t>(), sl.flag.as<uint32_t>(), 8000000000ll);
+        CU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(sl.h_out.p) + (size_t)ncols * 96, sl.flag.p, 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (readback) CU(cudaMemcpyAsync(sl.h_out.p, sl.out_canon.p, (size_t)ncols * 96, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (area && area->fetch) {
+        uint32_t timed_out = 0;
+        memcpy(&timed_out, reinterpret_cast<uint8_t*>(sl.h_out.p) + (size_t)ncols * 96, 4);
+        if (timed_out) return fail(B200ZK_ERR_CUDA, "exchange: a peer never delivered its partial sum (timed out)");
+    }
+    if (readback) memcpy(out, sl.h_out.p, (size_t)ncols * 96);
+    return B200ZK_OK;
+}
 
-int32_t b200zk_init(int32_t device) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g.inited) return B200ZK_OK;
+// The plan of one host-buffer MSM call over the bound devices.
+struct MsmPiece {
+    Ctx* c;
+    const TableShard* sh;
+    uint32_t col0, ncols;     // columns of the call this device computes
+    uint64_t i0, n;           // scalar index range of those columns
+    uint64_t bases_off;       // offset of point i0 inside the shard's table
+};
+
+int32_t msm_host(uint64_t bases, uint64_t offset, const ColSrc& src, uint64_t n, uint32_t batch, uint32_t scalar_fmt, uint8_t* out_affine) {
+    TRY(need_init());
+    if (!out_affine || (!src.ptrs && !src.base && !src.dev_slices && n && batch)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    if (scalar_fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown scalar format");
+    if (batch == 0) return B200ZK_OK;
+    if (src.ptrs && n)
+        for (uint32_t j = 0; j < batch; j++)
+            if (!src.ptrs[j]) return fail(B200ZK_ERR_INVALID_ARG, "null scalar column");
+    std::shared_ptr<TableSet> ts;
+    TRY(get_table(bases, offset, n, &ts));
+    if (n == 0) { memset(out_affine, 0, (size_t)batch * 96); return B200ZK_OK; }
+    const int D = (int)g_devs.size();
+    std::vector<MsmPiece> pieces;
+    bool exchange = false;
+    if (src.dev_slices && (ts->shards.size() == 1 || ts->replicated || offset != 0 || n != ts->n || batch != 1))
+        return fail(B200ZK_ERR_INVALID_ARG, "sharded_dev: needs a table partitioned over several GPUs and one full-length scalar vector sliced like it");
+    if (ts->shards.size() == 1) {
+        const TableShard& sh = ts->shards[0];
+        pieces.push_back({g_devs[sh.dev].get(), &sh, 0, batch, 0, n, offset - sh.start});
+    } else if (ts->replicated && (batch >= 2 || n < g_range_split_min)) {
+        // independent columns: deal them out in contiguous blocks, no exchange (a lone small MSM stays on one GPU)
+        int used = (int)std::min<uint32_t>(batch, (uint32_t)D);
+        static std::atomic<unsigned> rr{0};
+        unsigned first = batch == 1 ? rr.fetch_add(1) % (unsigned)D : 0;
+        for (int k = 0; k < used; k++) {
+            uint32_t b0 = (uint32_t)((uint64_t)batch * k / used), b1 = (uint32_t)((uint64_t)batch * (k + 1) / used);
+            const TableShard& sh = ts->shards[(first + k) % D];
+            pieces.push_back({g_devs[sh.dev].get(), &sh, b0, b1 - b0, 0, n, offset});
+        }
+    } else {
+        // point-range split with the partials meeting on the first GPU
+        exchange = true;
+        if (batch > XCHG_MAX_COLS) return fail(B200ZK_ERR_INVALID_ARG, "msm: more than 1024 columns in one sharded call; split the batch");
+        for (int k = 0; k < (int)ts->shards.size(); k++) {
+            const TableShard& sh = ts->shards[k];
+            uint64_t lo, hi;
+            if (ts->replicated) {
+                lo = offset + n * k / D;
+                hi = offset + n * (k + 1) / D;
+            } else {
+                lo = std::max(offset, sh.start);
+                hi = std::min(offset + n, sh.start + sh.n);
+                if (hi < lo) hi = lo;
+            }
+            // every device takes part in the exchange, an empty slice contributes the identity
+            pieces.push_back({g_devs[sh.dev].get(), &sh, 0, batch, lo - offset, hi - lo, (hi > lo ? lo : sh.start) - sh.start});
+        }
+    }
+    // slots in device order (ordered acquisition: concurrent multi-GPU calls cannot deadlock), then the meeting point
+    std::sort(pieces.begin(), pieces.end(), [](const MsmPiece& a, const MsmPiece& b) { return a.c->index < b.c->index; });
+    std::vector<SlotLease> leases;
+    for (auto& p : pieces) leases.emplace_back(*p.c);
+    XchgArea* area = nullptr;
+    if (exchange) {
+        area = acquire_area();
+        area->seq++;
+        area->n_parts = (uint32_t)pieces.size();
+    }
+    std::vector<Job> jobs;
+    std::vector<XchgArea> views(pieces.size());
+    for (size_t k = 0; k < pieces.size(); k++) {
+        MsmPiece* p = &pieces[k];
+        Slot* sl = leases[k].s;
+        XchgArea* view = nullptr;
+        if (area) {
+            views[k].base = area->base;
+            views[k].host_canon = area->host_canon;
+            views[k].n_parts = area->n_parts;
+            views[k].part = (uint32_t)k;
+            views[k].seq = area->seq;
+            view = &views[k];
+        }
+        uint8_t* out = out_affine + (size_t)p->col0 * 96;
+        jobs.push_back({p->c, [p, sl, &src, scalar_fmt, view, out]() -> int32_t {
+                            return msm_host_device(*p->c, *sl, &p->sh->t, p->bases_off, src, p->col0, p->ncols, p->i0, p->n, scalar_fmt, view, out);
+                        }});
+    }
+    int32_t rc = run_jobs(jobs);
+    if (area) {
+        if (rc == B200ZK_OK) memcpy(out_affine, area->host_canon, (size_t)batch * 96);   // every stream has been waited for
+        release_area(area);
+    }
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer NTT on one device: polynomials [p0, p0 + cnt) of the call
+// ------------------------------------------------------------------------------------------
+struct PolySrc {
+    uint8_t* const* ptrs = nullptr;
+    uint8_t* base = nullptr;
+};
+int32_t ntt_host_device(Ctx& c, Slot& sl, const PolySrc& src, uint32_t p0, uint32_t cnt, uint32_t log_n, const uint8_t omega[32],
+                        uint32_t flags, const uint8_t* coset_shift) {
+    if (cnt == 0) return B200ZK_OK;
+    const size_t poly = ((size_t)1 << log_n) * 32;
+    const size_t bytes = poly * cnt;
+    TRY(sl.ntt_data.ensure(bytes));
+    uint8_t* d = sl.ntt_data.as<uint8_t>();
+    cudaStream_t s = sl.stream;
+    auto copy_group = [&](uint32_t b0, uint32_t b1, bool up, cudaStream_t st) -> int32_t {
+        if (!src.ptrs) {
+            uint8_t* h = src.base + (size_t)(p0 + b0) * poly;
+            if (up) CU(cudaMemcpyAsync(d + b0 * poly, h, (size_t)(b1 - b0) * poly, cudaMemcpyHostToDevice, st));
+            else CU(cudaMemcpyAsync(h, d + b0 * poly, (size_t)(b1 - b0) * poly, cudaMemcpyDeviceToHost, st));
+            return B200ZK_OK;
+        }
+        for (uint32_t j = b0; j < b1; j++) {
+            if (up) CU(cudaMemcpyAsync(d + j * poly, src.ptrs[p0 + j], poly, cudaMemcpyHostToDevice, st));
+            else CU(cudaMemcpyAsync(src.ptrs[p0 + j], d + j * poly, poly, cudaMemcpyDeviceToHost, st));
+        }
+        return B200ZK_OK;
+    };
+    if (cnt >= 4 && g_ntt_pipe_min > 0 && bytes >= (size_t)g_ntt_pipe_min) {
+        // A transform is PCIe-bound end to end (2^22: 2.4 ms up, 0.94 ms of kernels, 2.4 ms down), and the link is full
+        // duplex: group g+1 goes up and group g-1 comes down while group g is transformed.
+        TRY(slot_streams(sl));
+        const uint32_t groups = std::min<uint32_t>(8, cnt / 2);
+        while (sl.pipe_up.size() < groups) {
+            cudaEvent_t e1, e2;
+            CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            sl.pipe_up.push_back(e1);
+            sl.pipe_done.push_back(e2);
+        }
+        for (uint32_t k = 0; k < groups; k++) {
+            const uint32_t b0 = (uint32_t)((uint64_t)cnt * k / groups), b1 = (uint32_t)((uint64_t)cnt * (k + 1) / groups);
+            TRY(copy_group(b0, b1, true, sl.copy_stream));
+            CU(cudaEventRecord(sl.pipe_up[k], sl.copy_stream));
+            CU(cudaStreamWaitEvent(s, sl.pipe_up[k], 0));
+            TRY(ntt_run(c, sl, reinterpret_cast<uint32_t*>(d + b0 * poly), b1 - b0, log_n, omega, flags, coset_shift, s));
+            CU(cudaEventRecord(sl.pipe_done[k], s));
+            CU(cudaStreamWaitEvent(sl.down_stream, sl.pipe_done[k], 0));
+            TRY(copy_group(b0, b1, false, sl.down_stream));
+        }
+        CU(cudaStreamSynchronize(sl.down_stream));
+        CU(cudaStreamSynchronize(s));
+        return B200ZK_OK;
+    }
+    TRY(copy_group(0, cnt, true, s));
+    TRY(ntt_run(c, sl, sl.ntt_data.as<uint32_t>(), cnt, log_n, omega, flags, coset_shift, s));
+    TRY(copy_group(0, cnt, false, s));
+    CU(cudaStreamSynchronize(s));
+    return B200ZK_OK;
+}
+
+int32_t ntt_host(const PolySrc& src, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags, const uint8_t* coset_shift) {
+    TRY(need_init());
+    if ((!src.ptrs && !src.base) || !omega) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    TRY(ntt_check_args(log_n, flags, coset_shift));
+    if (batch == 0) return B200ZK_OK;
+    if (src.ptrs)
+        for (uint32_t j = 0; j < batch; j++)
+            if (!src.ptrs[j]) return fail(B200ZK_ERR_INVALID_ARG, "null polynomial");
+    // independent polynomials: contiguous blocks per GPU, no exchange; each GPU's PCIe link carries its own block
+    const int D = (int)g_devs.size();
+    int used = (int)std::min<uint32_t>(batch, (uint32_t)D);
+    Ctx* first = nullptr;
+    TRY(current_ctx(&first));
+    struct Piece { Ctx* c; uint32_t p0, cnt; };
+    std::vector<Piece> pieces;
+    for (int k = 0; k < used; k++) {
+        uint32_t b0 = (uint32_t)((uint64_t)batch * k / used), b1 = (uint32_t)((uint64_t)batch * (k + 1) / used);
+        pieces.push_back({used == 1 ? first : g_devs[k].get(), b0, b1 - b0});
+    }
+    std::vector<SlotLease> leases;
+    for (auto& p : pieces) leases.emplace_back(*p.c);
+    std::vector<Job> jobs;
+    for (size_t k = 0; k < pieces.size(); k++) {
+        Piece* p = &pieces[k];
+        Slot* sl = leases[k].s;
+        jobs.push_back({p->c, [p, sl, &src, log_n, omega, flags, coset_shift]() -> int32_t {
+                            return ntt_host_device(*p->c, *sl, src, p->p0, p->cnt, log_n, omega, flags, coset_shift);
+                        }});
+    }
+    return run_jobs(jobs);
+}
+
+// ------------------------------------------------------------------------------------------
+// registration of one shard on one device
+// ------------------------------------------------------------------------------------------
+// h_src: host source of the whole table (or null); d_src / src_ordinal: device source of the whole table (or null)
+int32_t register_shard(Ctx& c, TableShard& sh, const uint8_t* h_src, const uint8_t* d_src, int src_ordinal, uint32_t fmt_flags,
+                       uint32_t stride) {
+    BaseTable& t = sh.t;
+    const uint64_t n = sh.n;
+    t.n = n;
+    uint32_t fmt = fmt_flags & 0xffu;
+    cudaStream_t s = c.stream;
+    // Window tables: W rows of n points.  Built for resident SRS tables of >= 1024 points (they are registered once and
+    // committed against many times); skipped on request, for small tables, or when HBM is short.
+    bool want_rows = !(fmt_flags & B200ZK_BASES_NO_WINDOW_TABLES) && !g_tune_no_tables && n >= 1024;
+    uint32_t cbits = 0, W = 1;
+    if (want_rows) {
+        cbits = (g_tune_c >= 2 && g_tune_c <= 24) ? g_tune_c : std::max(msm_choose_window(n, 1, true), 8u);   // c >= 8: at most 32 rows
+        W = (256 + cbits - 1) / cbits;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if ((double)W * n * 96.0 > 0.45 * (double)free_b || (double)W * n >= 2147483648.0 || W > (uint32_t)MSM_MAX_ROWS) { W = 1; cbits = 0; }
+    }
+    const uint8_t* d_in = nullptr;
+    if (n) {
+        size_t bytes = (size_t)(n - 1) * stride + 96;
+        const size_t off = (size_t)sh.start * stride;
+        if (h_src) {
+            TRY(c.reg_stage.ensure(bytes + 16));
+            CU(cudaMemcpyAsync(c.reg_stage.p, h_src + off, bytes, cudaMemcpyHostToDevice, s));
+            d_in = c.reg_stage.as<uint8_t>();
+        } else if (src_ordinal == c.ordinal) {
+            d_in = d_src + off;
+        } else {
+            TRY(c.reg_stage.ensure(bytes + 16));
+            CU(cudaMemcpyPeerAsync(c.reg_stage.p, c.ordinal, d_src + off, src_ordinal, bytes, s));
+            d_in = c.reg_stage.as<uint8_t>();
+        }
+    }
+    CU(cudaMalloc(&t.d, std::max<uint64_t>(n, 1) * 96 * W));
+    int32_t rc = n ? ingest_bases(c, d_in, n, fmt, stride, t.d, s) : B200ZK_OK;
+    if (rc != B200ZK_OK) { cudaFree(t.d); t.d = nullptr; return rc; }
+    if (W > 1) {
+        g1_window_tables_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(t.d, n, cbits, W);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { cudaFree(t.d); t.d = nullptr; return fail(B200ZK_ERR_CUDA, std::string("window tables: ") + cudaGetErrorString(e)); }
+        t.rows = W;
+        t.c = cbits;
+    }
+    return B200ZK_OK;
+}
+
+int32_t register_common(const uint8_t* h_src, const uint8_t* d_src, uint64_t n, uint32_t fmt_flags, uint32_t stride_bytes,
+                        uint64_t* out_handle) {
+    TRY(need_init());
+    if (!out_handle || (!h_src && !d_src && n)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    if ((fmt_flags & 0xffu) > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown point format");
+    if ((fmt_flags & B200ZK_BASES_SHARD) && (fmt_flags & B200ZK_BASES_REPLICATE))
+        return fail(B200ZK_ERR_INVALID_ARG, "B200ZK_BASES_SHARD and B200ZK_BASES_REPLICATE are mutually exclusive");
+    uint32_t stride = stride_bytes ? stride_bytes : 96;
+    if (stride < 96 || (stride & 3)) return fail(B200ZK_ERR_INVALID_ARG, "stride must be >= 96 and a multiple of 4");
+    const int D = (int)g_devs.size();
+    int src_ordinal = -1;
+    Ctx* home = nullptr;
+    if (d_src) {
+        TRY(ctx_for_pointer(d_src, &home));
+        src_ordinal = home->ordinal;
+        DeviceScope ds(home->ordinal);
+        CU(cudaDeviceSynchronize());   // the source may have been produced on another stream
+    } else {
+        TRY(current_ctx(&home));
+    }
+    auto ts = std::make_shared<TableSet>();
+    ts->n = n;
+    if (D == 1 || n < (uint64_t)D) {
+        ts->shards.resize(1);
+        ts->shards[0].dev = home->index;
+        ts->shards[0].start = 0;
+        ts->shards[0].n = n;
+    } else {
+        // small tables are replicated (a batch of columns is dealt out over the GPUs), large ones partitioned by point range
+        bool replicate = (fmt_flags & B200ZK_BASES_REPLICATE) != 0;
+        if (!(fmt_flags & (B200ZK_BASES_REPLICATE | B200ZK_BASES_SHARD))) {
+            uint32_t W = (fmt_flags & B200ZK_BASES_NO_WINDOW_TABLES) ? 1 : 16;
+            replicate = (double)n * 96.0 * W <= (double)g_replicate_max_bytes;
+        }
+        ts->replicated = replicate;
+        ts->shards.resize(D);
+        for (int k = 0; k < D; k++) {
+            ts->shards[k].dev = k;
+            ts->shards[k].start = replicate ? 0 : n * k / D;
+            ts->shards[k].n = replicate ? n : n * (k + 1) / D - n * k / D;
+        }
+    }
+    std::vector<Job> jobs;
+    for (auto& shr : ts->shards) {
+        TableShard* sh = &shr;
+        Ctx* c = g_devs[sh->dev].get();
+        jobs.push_back({c, [c, sh, h_src, d_src, src_ordinal, fmt_flags, stride]() -> int32_t {
+                            std::lock_guard<std::mutex> lk(c->mu);   // c.reg_stage / c.reg_flag / c.stream
+                            return register_shard(*c, *sh, h_src, d_src, src_ordinal, fmt_flags, stride);
+                        }});
+    }
+    int32_t rc = run_jobs(jobs);
+    if (rc != B200ZK_OK) {
+        for (auto& sh : ts->shards)
+            if (sh.t.d) { DeviceScope ds(g_devs[sh.dev]->ordinal); cudaFree(sh.t.d); }
+        return rc;
+    }
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    uint64_t h = g_next_handle++;
+    g_tables[h] = ts;
+    *out_handle = h;
+    return B200ZK_OK;
+}
+
+int32_t init_devices_locked(const int32_t* ids, int32_t n) {
+    if (!g_devs.empty()) return B200ZK_OK;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -843,61 +1389,217 @@ int32_t b200zk_init(int32_t device) {
         return fail(B200ZK_ERR_NO_DEVICE,
                     std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
     }
-    if (device < 0) {
-        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    if (n < 1 || n > (int32_t)XCHG_MAX_PARTS) return fail(B200ZK_ERR_INVALID_ARG, "between 1 and 16 devices can be bound");
+    std::vector<int> ords;
+    for (int i = 0; i < n; i++) {
+        int d = ids ? ids[i] : i;
+        if (d < 0) {
+            if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+        }
+        if (d >= count) return fail(B200ZK_ERR_NO_DEVICE, "device index out of range");
+        if (std::find(ords.begin(), ords.end(), d) != ords.end()) return fail(B200ZK_ERR_INVALID_ARG, "a device is listed twice");
+        ords.push_back(d);
     }
-    if (device >= count) return fail(B200ZK_ERR_NO_DEVICE, "device index out of range");
-    CU(cudaSetDevice(device));
-    CU(cudaGetDeviceProperties(&g.prop, device));
-    if (g.prop.major != 10)
-        return fail(B200ZK_ERR_NO_DEVICE, std::string("device '") + g.prop.name +
-                                              "' is not sm_100: this library ships sm_100a code only and has no fallback");
-    CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    g.device = device;
-    g.inited = true;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    read_env();
+    std::vector<std::unique_ptr<Ctx>> devs;
+    auto undo = [&](int32_t rc) {
+        for (auto& c : devs) {
+            cudaSetDevice(c->ordinal);
+            for (Slot& sl : c->slots)
+                if (sl.stream) cudaStreamDestroy(sl.stream);
+            if (c->stream) cudaStreamDestroy(c->stream);
+        }
+        if (prev >= 0) cudaSetDevice(prev);
+        return rc;
+    };
+    for (int i = 0; i < n; i++) {
+        auto c = std::make_unique<Ctx>();
+        c->ordinal = ords[i];
+        c->index = i;
+        cudaError_t e2 = cudaSetDevice(c->ordinal);
+        if (e2 == cudaSuccess) e2 = cudaGetDeviceProperties(&c->prop, c->ordinal);
+        if (e2 != cudaSuccess) return undo(fail(B200ZK_ERR_CUDA, std::string("cannot bind device: ") + cudaGetErrorString(e2)));
+        if (c->prop.major != 10)
+            return undo(fail(B200ZK_ERR_NO_DEVICE, std::string("device '") + c->prop.name +
+                                                       "' is not sm_100: this library ships sm_100a code only and has no fallback"));
+        e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        for (int k = 0; k < NSLOT && e2 == cudaSuccess; k++) {
+            c->slots[k].id = k;
+            e2 = cudaStreamCreateWithFlags(&c->slots[k].stream, cudaStreamNonBlocking);
+        }
+        devs.push_back(std::move(c));
+        if (e2 != cudaSuccess) return undo(fail(B200ZK_ERR_CUDA, std::string("stream creation failed: ") + cudaGetErrorString(e2)));
+    }
+    if (n > 1) {
+        // every pair of bound GPUs can reach each other's HBM (NVLink / NVSwitch): the exchange of partial sums and the
+        // transposes of the multi-GPU NTT are plain stores into a peer's memory
+        for (int i = 0; i < n; i++) {
+            cudaSetDevice(ords[i]);
+            for (int j = 0; j < n; j++) {
+                if (i == j) continue;
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, ords[i], ords[j]);
+                if (!can) return undo(fail(B200ZK_ERR_NO_DEVICE, "GPUs " + std::to_string(ords[i]) + " and " + std::to_string(ords[j]) +
+                                                                     " have no peer access: the multi-GPU paths need NVLink / PCIe P2P"));
+                cudaError_t e3 = cudaDeviceEnablePeerAccess(ords[j], 0);
+                if (e3 == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e3 != cudaSuccess) return undo(fail(B200ZK_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e3)));
+            }
+        }
+        cudaSetDevice(ords[0]);
+        for (auto& a : g_areas) {
+            cudaError_t e3 = cudaMalloc(&a.base, XchgArea::bytes());
+            if (e3 == cudaSuccess) e3 = cudaMemset(a.base, 0, XchgArea::bytes());
+            if (e3 == cudaSuccess) e3 = cudaHostAlloc((void**)&a.host_canon, 96 * (size_t)XCHG_MAX_COLS, cudaHostAllocPortable | cudaHostAllocMapped);
+            if (e3 != cudaSuccess) return undo(fail(B200ZK_ERR_CUDA, std::string("exchange area: ") + cudaGetErrorString(e3)));
+            a.owner = true;
+            a.busy = false;
+            a.seq = 0;
+            a.home_ordinal = ords[0];
+        }
+    }
+    g_devs = std::move(devs);
+    if (g_devs.size() > 1)
+        for (auto& c : g_devs) c->worker.start(c->ordinal);
+    if (prev >= 0) cudaSetDevice(prev);
+    return B200ZK_OK;
+}
+
+}  // namespace
+
+// what the other translation units share with these contexts (ctx.hpp)
+namespace b200zk_ctx {
+int32_t fail(int32_t code, const std::string& msg) { return ::fail(code, msg); }
+int32_t current(Dev** out) { return ::current_ctx(out); }
+int32_t for_pointer(const void* p, Dev** out) { return ::ctx_for_pointer(p, out); }
+int32_t by_index(int index, Dev** out) {
+    XTRY(::need_init());
+    if (index < 0 || index >= (int)g_devs.size()) return ::fail(B200ZK_ERR_BAD_HANDLE, "handle names a device that is not bound");
+    *out = g_devs[index].get();
+    return B200ZK_OK;
+}
+int device_count() { return (int)g_devs.size(); }
+int ordinal(Dev* d) { return d->ordinal; }
+int index(Dev* d) { return d->index; }
+std::mutex& mutex(Dev* d) { return d->mu; }
+cudaStream_t stream(Dev* d) { return d->stream; }
+int sm_count(Dev* d) { return d->prop.multiProcessorCount; }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int32_t generator_dev(Dev* d, uint32_t** out, cudaStream_t s) { return get_generator_dev(*d, out, s); }
+void on_shutdown(void (*fn)()) { g_hooks.push_back(fn); }
+int32_t ws_enter(Dev* d, cudaStream_t s) {
+    if (!d->ws_event) XCU(cudaEventCreateWithFlags(&d->ws_event, cudaEventDisableTiming));
+    if (d->ws_used && s != d->ws_stream) XCU(cudaStreamWaitEvent(s, d->ws_event, 0));
+    return B200ZK_OK;
+}
+int32_t ws_leave(Dev* d, cudaStream_t s) {
+    XCU(cudaEventRecord(d->ws_event, s));
+    d->ws_stream = s;
+    d->ws_used = true;
+    return B200ZK_OK;
+}
+}  // namespace b200zk_ctx
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+int32_t b200zk_init_devices(const int32_t* device_ids, int32_t n_devices) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return init_devices_locked(device_ids, n_devices);
+}
+
+int32_t b200zk_init(int32_t device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return init_devices_locked(&device, 1);
+}
+
+int32_t b200zk_device_count(void) { return (int32_t)g_devs.size(); }
+
+int32_t b200zk_set_device(int32_t index) {
+    TRY(need_init());
+    if (index < 0 || index >= (int32_t)g_devs.size()) return fail(B200ZK_ERR_INVALID_ARG, "device index outside the bound devices");
+    t_dev_index = index;
     return B200ZK_OK;
 }
 
 int32_t b200zk_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g.inited) return B200ZK_OK;
-    cudaSetDevice(g.device);
-    cudaDeviceSynchronize();
-    for (auto fn : b200zk_ctx::g_hooks) fn();
-    for (auto& kv : g.tables) cudaFree(kv.second.d);
-    g.tables.clear();
-    for (auto& kv : g.ntt_plans) {
-        for (int i = 0; i < 3; i++) {
-            if (kv.second.tw_local[i]) cudaFree(kv.second.tw_local[i]);
-            if (kv.second.tw_pass[i]) cudaFree(kv.second.tw_pass[i]);
+    if (g_devs.empty()) return B200ZK_OK;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (auto& c : g_devs) c->worker.shutdown();
+    for (auto& c : g_devs) {
+        cudaSetDevice(c->ordinal);
+        cudaDeviceSynchronize();
+    }
+    for (auto fn : g_hooks) fn();
+    {
+        std::lock_guard<std::mutex> lt(g_tab_mu);
+        for (auto& kv : g_tables)
+            for (auto& sh : kv.second->shards) {
+                cudaSetDevice(g_devs[sh.dev]->ordinal);
+                cudaFree(sh.t.d);
+            }
+        g_tables.clear();
+    }
+    {
+        std::lock_guard<std::mutex> la(g_area_mu);
+        for (auto& kv : g_xchg) {
+            XchgArea& a = *kv.second;
+            cudaSetDevice(a.home_ordinal);
+            if (a.ipc && a.base) cudaIpcCloseMemHandle(a.base);
+            else if (a.base) cudaFree(a.base);
+            a.status.release();
         }
-        if (kv.second.ninv) cudaFree(kv.second.ninv);
+        g_xchg.clear();
+        for (auto& a : g_areas) {
+            if (a.base) { cudaSetDevice(a.home_ordinal); cudaFree(a.base); }
+            if (a.host_canon) cudaFreeHost(a.host_canon);
+            a = XchgArea();
+        }
     }
-    g.ntt_plans.clear();
-    for (auto& kv : g.coset_tables) cudaFree(kv.second);
-    g.coset_tables.clear();
-    if (g.fixed_table) { cudaFree(g.fixed_table); g.fixed_table = nullptr; }
-    DevBuf* all[] = {&g.scalars, &g.counts, &g.offsets, &g.cursor, &g.ntask, &g.task_off, &g.entries, &g.task_bucket,
-                     &g.task_start, &g.task_len, &g.buckets, &g.partials, &g.len_hist, &g.len_off, &g.order, &g.heavy, &g.heavy_items, &g.adhoc, &g.buckets2, &g.aff_a, &g.aff_b, &g.aff_pre, &g.redS[0], &g.redS[1], &g.redA[0], &g.redA[1],
-                     &g.scan_tmp[0], &g.scan_tmp[1], &g.out_mont, &g.out_canon, &g.stage, &g.flag, &g.ntt_data,
-                     &g.ntt_tmp[0], &g.ntt_tmp[1], &g.small};
-    for (DevBuf* b : all) b->release();
-    if (g.down_stream) { cudaStreamDestroy(g.down_stream); g.down_stream = nullptr; }
-    for (cudaEvent_t e : g.pipe_up) cudaEventDestroy(e);
-    for (cudaEvent_t e : g.pipe_done) cudaEventDestroy(e);
-    g.pipe_up.clear();
-    g.pipe_done.clear();
-    if (g.copy_stream) {
-        cudaStreamDestroy(g.copy_stream);
-        cudaEventDestroy(g.copy_ev[0]);
-        cudaEventDestroy(g.copy_ev[1]);
-        g.copy_stream = nullptr;
+    for (auto& cp : g_devs) {
+        Ctx& c = *cp;
+        cudaSetDevice(c.ordinal);
+        for (auto& kv : c.ntt_plans) {
+            for (int i = 0; i < 3; i++) {
+                if (kv.second.tw_local[i]) cudaFree(kv.second.tw_local[i]);
+                if (kv.second.tw_pass[i]) cudaFree(kv.second.tw_pass[i]);
+            }
+            if (kv.second.ninv) cudaFree(kv.second.ninv);
+        }
+        for (auto& kv : c.coset_tables) cudaFree(kv.second);
+        if (c.fixed_table) cudaFree(c.fixed_table);
+        if (c.d_gen) cudaFree(c.d_gen);
+        c.reg_stage.release();
+        c.reg_flag.release();
+        for (Slot& sl : c.slots) {
+            for (DevBuf* b : sl.all()) b->release();
+            sl.h_out.release();
+            for (cudaEvent_t e : sl.pipe_up) cudaEventDestroy(e);
+            for (cudaEvent_t e : sl.pipe_done) cudaEventDestroy(e);
+            for (cudaEvent_t e : sl.ev)
+                if (e) cudaEventDestroy(e);
+            if (sl.copy_stream) {
+                cudaStreamDestroy(sl.copy_stream);
+                cudaEventDestroy(sl.copy_ev[0]);
+                cudaEventDestroy(sl.copy_ev[1]);
+            }
+            if (sl.down_stream) cudaStreamDestroy(sl.down_stream);
+            if (sl.ws_event) cudaEventDestroy(sl.ws_event);
+            if (sl.stream) cudaStreamDestroy(sl.stream);
+        }
+        if (c.ws_event) cudaEventDestroy(c.ws_event);
+        if (c.stream) cudaStreamDestroy(c.stream);
     }
-    if (g.ws_event) { cudaEventDestroy(g.ws_event); g.ws_event = nullptr; }
-    g.ws_used = false;
-    if (g.stream) cudaStreamDestroy(g.stream);
-    g.stream = nullptr;
-    g.inited = false;
+    g_devs.clear();
+    g_prof_ctx = nullptr;
+    g_prof_slot = nullptr;
+    if (prev >= 0) cudaSetDevice(prev);
     return B200ZK_OK;
 }
 
@@ -908,186 +1610,89 @@ int32_t b200zk_last_error(char* buf, size_t len) {
 }
 
 int32_t b200zk_device_info(char* buf, size_t len) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(need_init());
+    Ctx* c = nullptr;
+    TRY(current_ctx(&c));
     if (!buf || len == 0) return fail(B200ZK_ERR_INVALID_ARG, "null buffer");
-    snprintf(buf, len, "%s sm_%d%d %dSM", g.prop.name, g.prop.major, g.prop.minor, g.prop.multiProcessorCount);
+    snprintf(buf, len, "%s sm_%d%d %dSM", c->prop.name, c->prop.major, c->prop.minor, c->prop.multiProcessorCount);
     return B200ZK_OK;
 }
 
 int32_t b200zk_host_alloc(void** out, size_t bytes) {
-    std::lock_guard<std::mutex> lk(g_mu);
     TRY(need_init());
     if (!out) return fail(B200ZK_ERR_INVALID_ARG, "null out pointer");
-    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));   // pinned for every bound GPU
     return B200ZK_OK;
 }
 int32_t b200zk_host_free(void* p) {
-    std::lock_guard<std::mutex> lk(g_mu);
     TRY(need_init());
     if (p) CU(cudaFreeHost(p));
     return B200ZK_OK;
 }
 
-static int32_t register_common(const uint8_t* d_src, uint64_t n, uint32_t fmt_flags, uint32_t stride, uint64_t* out_handle) {
-    BaseTable t;
-    t.n = n;
-    uint32_t fmt = fmt_flags & 0xffu;
-    // Window tables: W rows of n points.  Built for resident SRS tables (they are registered once and
-    // committed against many times); skipped on request, for tiny tables, or when HBM is short.
-    bool want_rows = !(fmt_flags & B200ZK_BASES_NO_WINDOW_TABLES) && !g.tune_no_tables && n >= 1;
-    uint32_t c = 0, W = 1;
-    if (want_rows) {
-        c = (g.tune_c >= 2 && g.tune_c <= 24) ? g.tune_c : std::max(msm_choose_window(n, 1, true), 8u);   // c >= 8: at most 32 rows
-        W = (256 + c - 1) / c;
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        if ((double)W * n * 96.0 > 0.45 * (double)free_b || (double)W * n >= 2147483648.0 || W > (uint32_t)MSM_MAX_ROWS) { W = 1; c = 0; }
-    }
-    CU(cudaMalloc(&t.d, std::max<uint64_t>(n, 1) * 96 * W));
-    int32_t rc = n ? ingest_bases(d_src, n, fmt, stride, t.d, g.stream) : B200ZK_OK;
-    if (rc != B200ZK_OK) { cudaFree(t.d); return rc; }
-    if (W > 1) {
-        g1_window_tables_kernel<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(t.d, n, c, W);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
-        if (e != cudaSuccess) { cudaFree(t.d); return fail(B200ZK_ERR_CUDA, std::string("window tables: ") + cudaGetErrorString(e)); }
-        t.rows = W;
-        t.c = c;
-    }
-    uint64_t h = g.next_handle++;
-    g.tables[h] = t;
-    *out_handle = h;
-    return B200ZK_OK;
+int32_t b200zk_bases_register(const uint8_t* g1_affine, uint64_t n, uint32_t fmt, uint32_t stride_bytes, uint64_t* out_handle) {
+    return register_common(g1_affine, nullptr, n, fmt, stride_bytes, out_handle);
 }
 
-int32_t b200zk_bases_register(const uint8_t* g1_affine, uint64_t n, uint32_t fmt, uint32_t stride_bytes,
-                              uint64_t* out_handle) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(need_init());
-    if (!out_handle || (!g1_affine && n)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
-    if ((fmt & 0xffu) > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown point format");
-    uint32_t stride = stride_bytes ? stride_bytes : 96;
-    if (stride < 96 || (stride & 3)) return fail(B200ZK_ERR_INVALID_ARG, "stride must be >= 96 and a multiple of 4");
-    size_t bytes = n ? (size_t)(n - 1) * stride + 96 : 0;
-    TRY(g.stage.ensure(bytes + 16));
-    if (bytes) CU(cudaMemcpyAsync(g.stage.p, g1_affine, bytes, cudaMemcpyHostToDevice, g.stream));
-    return register_common(g.stage.as<uint8_t>(), n, fmt, stride, out_handle);
-}
-
-int32_t b200zk_bases_register_dev(const void* d_g1_affine, uint64_t n, uint32_t fmt, uint32_t stride_bytes,
-                                  uint64_t* out_handle) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(need_init());
-    if (!out_handle || (!d_g1_affine && n)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
-    if ((fmt & 0xffu) > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown point format");
-    uint32_t stride = stride_bytes ? stride_bytes : 96;
-    if (stride < 96 || (stride & 3)) return fail(B200ZK_ERR_INVALID_ARG, "stride must be >= 96 and a multiple of 4");
-    CU(cudaDeviceSynchronize());  // the source may have been produced on another stream
-    return register_common(reinterpret_cast<const uint8_t*>(d_g1_affine), n, fmt, stride, out_handle);
+int32_t b200zk_bases_register_dev(const void* d_g1_affine, uint64_t n, uint32_t fmt, uint32_t stride_bytes, uint64_t* out_handle) {
+    return register_common(nullptr, reinterpret_cast<const uint8_t*>(d_g1_affine), n, fmt, stride_bytes, out_handle);
 }
 
 int32_t b200zk_bases_release(uint64_t handle) {
-    std::lock_guard<std::mutex> lk(g_mu);
     TRY(need_init());
-    auto it = g.tables.find(handle);
-    if (it == g.tables.end()) return fail(B200ZK_ERR_BAD_HANDLE, "unknown base-table handle");
-    CU(cudaDeviceSynchronize());
-    cudaFree(it->second.d);
-    g.tables.erase(it);
+    std::shared_ptr<TableSet> ts;
+    {
+        std::lock_guard<std::mutex> lk(g_tab_mu);
+        auto it = g_tables.find(handle);
+        if (it == g_tables.end()) return fail(B200ZK_ERR_BAD_HANDLE, "unknown base-table handle");
+        ts = it->second;
+        g_tables.erase(it);
+    }
+    for (auto& sh : ts->shards) {
+        DeviceScope ds(g_devs[sh.dev]->ordinal);
+        CU(cudaDeviceSynchronize());
+        cudaFree(sh.t.d);
+        sh.t.d = nullptr;
+    }
     return B200ZK_OK;
 }
 
 int32_t b200zk_bases_read(uint64_t handle, uint64_t start, uint64_t n, uint8_t* out_affine) {
-    std::lock_guard<std::mutex> lk(g_mu);
     TRY(need_init());
-    const uint32_t* d = nullptr;
-    TRY(lookup_bases(handle, start, n, &d));
+    std::shared_ptr<TableSet> ts;
+    TRY(get_table(handle, start, n, &ts));
     if (n == 0) return B200ZK_OK;
     if (!out_affine) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
-    TRY(g.stage.ensure(n * 96));
-    LAUNCH(g1_export_kernel, (unsigned)((n + 127) / 128), 128, 0, g.stream, d, n, g.stage.as<uint32_t>());
-    CU(cudaMemcpyAsync(out_affine, g.stage.p, n * 96, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
+    for (const TableShard& sh : ts->shards) {
+        uint64_t lo = std::max(start, sh.start), hi = std::min(start + n, sh.start + sh.n);
+        if (hi <= lo) continue;
+        Ctx& c = *g_devs[sh.dev];
+        DeviceScope ds(c.ordinal);
+        std::lock_guard<std::mutex> lk(c.mu);
+        uint64_t cnt = hi - lo;
+        TRY(c.reg_stage.ensure(cnt * 96));
+        LAUNCH(g1_export_kernel, (unsigned)((cnt + 127) / 128), 128, 0, c.stream, (const uint32_t*)(sh.t.d + 24 * (lo - sh.start)), cnt,
+               c.reg_stage.as<uint32_t>());
+        CU(cudaMemcpyAsync(out_affine + (lo - start) * 96, c.reg_stage.p, cnt * 96, cudaMemcpyDeviceToHost, c.stream));
+        CU(cudaStreamSynchronize(c.stream));
+        if (ts->replicated) break;
+    }
     return B200ZK_OK;
 }
 
 int32_t b200zk_msm_g1_batch(uint64_t bases, uint64_t offset, const uint8_t* scalars, uint64_t n, uint32_t batch,
                             uint32_t scalar_fmt, uint8_t* out_affine) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(need_init());
-    if (!out_affine || (!scalars && n && batch)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
-    if (scalar_fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown scalar format");
-    if (batch == 0) return B200ZK_OK;
-    const uint32_t* d_bases = nullptr;
-    const BaseTable* tab = nullptr;
-    TRY(lookup_bases(bases, offset, n, &d_bases, &tab));
-    size_t bytes = (size_t)n * batch * 32;
-    TRY(g.scalars.ensure(bytes + 16));
-    TRY(g.out_canon.ensure((size_t)batch * 96));
-    static int64_t chunk_min = -1;   // a single MSM of at least this many points streams its scalars in two pieces
-    if (chunk_min < 0) { const char* v = getenv("B200ZK_MSM_CHUNK_MIN"); chunk_min = v ? atoll(v) : (1ll << 23); }
-    // batches of columns: worth two passes only when the transfer is long (measured: 75 MB at k = 17 loses 0.7 ms, 288 MB at
-    // k = 19 gains 3.3 ms)
-    static size_t batch_stream_min = 0;
-    if (!batch_stream_min) { const char* v = getenv("B200ZK_BATCH_STREAM_MIN_BYTES"); batch_stream_min = v ? (size_t)atoll(v) : ((size_t)128 << 20); if (!batch_stream_min) batch_stream_min = 1; }
-    if (batch == 1 && chunk_min > 0 && n >= (uint64_t)chunk_min) {
-        // The second piece of the scalars crosses PCIe while the first is sorted and accumulated: the first piece's
-        // buckets are g.buckets, the second accumulates into g.buckets2 and is folded in before the tail.
-        if (!g.copy_stream) {
-            CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&g.copy_ev[0], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&g.copy_ev[1], cudaEventDisableTiming));
-        }
-        // first piece = 1/8 of the points: its copy (1.2 ms at 2^24) is the only exposed transfer, and its sort + accumulate
-        // (9 ms) cover the copy of the other 7/8 (8.5 ms).  Measured at 2^24: 84.9 ms unchunked, 83.1 ms with halves.
-        // From pageable memory (a plain Rust Vec) the copy runs at ~11 GB/s instead of ~55: the balance point
-        // copy(rest) = compute(first) moves from 1/8 to 3/8 (measured at 2^24, pageable: 122.8 ms unchunked, 118.7 with 1/8).
-        cudaPointerAttributes pa{};
-        bool pinned = cudaPointerGetAttributes(&pa, scalars) == cudaSuccess && pa.type == cudaMemoryTypeHost;
-        cudaGetLastError();
-        const uint64_t nA = ((pinned ? n / 8 : 3 * (n / 8)) + 255) & ~(uint64_t)255, nB = n - nA;
-        uint8_t* d_sc = g.scalars.as<uint8_t>();
-        // (the first piece's kernels are enqueued before the second copy is issued: from pageable host memory a copy
-        // blocks the calling thread, and the device must already have work by then)
-        MsmChunk ca{n, 0, true, false}, cb{n, nA, false, true};
-        CU(cudaMemcpyAsync(d_sc, scalars, nA * 32, cudaMemcpyHostToDevice, g.copy_stream));
-        CU(cudaEventRecord(g.copy_ev[0], g.copy_stream));
-        CU(cudaStreamWaitEvent(g.stream, g.copy_ev[0], 0));
-        TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>(), nA, 1, scalar_fmt, nullptr, nullptr, g.stream, nullptr, &ca));
-        CU(cudaMemcpyAsync(d_sc + nA * 32, scalars + nA * 32, nB * 32, cudaMemcpyHostToDevice, g.copy_stream));
-        CU(cudaEventRecord(g.copy_ev[1], g.copy_stream));
-        CU(cudaStreamWaitEvent(g.stream, g.copy_ev[1], 0));
-        TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>() + 8 * nA, nB, 1, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream,
-                    nullptr, &cb));
-    } else if (batch >= 4 && chunk_min > 0 && bytes >= batch_stream_min) {
-        // The prover's pattern (all columns of a phase in one call): the columns are independent, so the first eighth of
-        // them goes up and starts computing while the others cross PCIe; no merge is needed.
-        if (!g.copy_stream) {
-            CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&g.copy_ev[0], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&g.copy_ev[1], cudaEventDisableTiming));
-        }
-        const uint32_t bA = std::max(1u, batch / 8), bB = batch - bA;
-        const size_t col = (size_t)n * 32;
-        uint8_t* d_sc = g.scalars.as<uint8_t>();
-        CU(cudaMemcpyAsync(d_sc, scalars, bA * col, cudaMemcpyHostToDevice, g.copy_stream));
-        CU(cudaEventRecord(g.copy_ev[0], g.copy_stream));
-        CU(cudaStreamWaitEvent(g.stream, g.copy_ev[0], 0));
-        TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>(), n, bA, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream));
-        CU(cudaMemcpyAsync(d_sc + bA * col, scalars + bA * col, bB * col, cudaMemcpyHostToDevice, g.copy_stream));
-        CU(cudaEventRecord(g.copy_ev[1], g.copy_stream));
-        CU(cudaStreamWaitEvent(g.stream, g.copy_ev[1], 0));
-        TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>() + 8 * (size_t)n * bA, n, bB, scalar_fmt, nullptr,
-                    g.out_canon.as<uint32_t>() + 24 * (size_t)bA, g.stream));
-    } else {
-        if (bytes) CU(cudaMemcpyAsync(g.scalars.p, scalars, bytes, cudaMemcpyHostToDevice, g.stream));
-        TRY(msm_run(tab, d_bases, g.scalars.as<uint32_t>(), n, batch, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), g.stream));
-    }
-    CU(cudaMemcpyAsync(out_affine, g.out_canon.p, (size_t)batch * 96, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
-    return B200ZK_OK;
+    ColSrc src;
+    src.base = scalars;
+    src.stride = (size_t)n * 32;
+    return msm_host(bases, offset, src, n, batch, scalar_fmt, out_affine);
+}
+
+int32_t b200zk_msm_g1_batch_ptrs(uint64_t bases, uint64_t offset, const uint8_t* const* scalars, uint64_t n, uint32_t batch,
+                                 uint32_t scalar_fmt, uint8_t* out_affine) {
+    if (!scalars && batch) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    ColSrc src;
+    src.ptrs = scalars;
+    return msm_host(bases, offset, src, n, batch, scalar_fmt, out_affine);
 }
 
 int32_t b200zk_msm_g1(uint64_t bases, uint64_t offset, const uint8_t* scalars, uint64_t n, uint32_t scalar_fmt,
@@ -1095,150 +1700,349 @@ int32_t b200zk_msm_g1(uint64_t bases, uint64_t offset, const uint8_t* scalars, u
     return b200zk_msm_g1_batch(bases, offset, scalars, n, 1, scalar_fmt, out_affine);
 }
 
+int32_t b200zk_bases_layout(uint64_t bases, uint32_t cap, uint32_t* out_n_shards, int32_t* out_device, uint64_t* out_start, uint64_t* out_n,
+                            uint32_t* out_replicated) {
+    TRY(need_init());
+    if (!out_n_shards) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    auto ts = find_table(bases);
+    if (!ts) return fail(B200ZK_ERR_BAD_HANDLE, "unknown base-table handle");
+    *out_n_shards = (uint32_t)ts->shards.size();
+    if (out_replicated) *out_replicated = ts->replicated ? 1u : 0u;
+    for (uint32_t k = 0; k < ts->shards.size() && k < cap; k++) {
+        if (out_device) out_device[k] = ts->shards[k].dev;
+        if (out_start) out_start[k] = ts->shards[k].start;
+        if (out_n) out_n[k] = ts->shards[k].n;
+    }
+    return B200ZK_OK;
+}
+
+int32_t b200zk_msm_g1_sharded_dev(uint64_t bases, const void* const* d_scalar_slices, uint32_t n_slices, uint32_t scalar_fmt,
+                                  uint8_t out_affine[96]) {
+    TRY(need_init());
+    if (!d_scalar_slices || !out_affine) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    auto ts = find_table(bases);
+    if (!ts) return fail(B200ZK_ERR_BAD_HANDLE, "unknown base-table handle");
+    if (n_slices != ts->shards.size()) return fail(B200ZK_ERR_INVALID_ARG, "sharded_dev: one scalar slice per shard of the table");
+    for (uint32_t k = 0; k < n_slices; k++)
+        if ((!d_scalar_slices[k] && ts->shards[k].n) || ((uintptr_t)d_scalar_slices[k] & 15))
+            return fail(B200ZK_ERR_INVALID_ARG, "sharded_dev: null or misaligned slice");
+    ColSrc src;
+    src.dev_slices = d_scalar_slices;
+    return msm_host(bases, 0, src, ts->n, 1, scalar_fmt, out_affine);
+}
+
+// points [i0, i0 + n) of an ad-hoc sum on one device: upload, on-curve check, MSM; the result (or, with an exchange, the
+// partial sum) leaves through the usual paths.  *bad = 1 if a point was rejected.
+static int32_t adhoc_device(Ctx& c, Slot& sl, const uint8_t* g1_affine, uint32_t point_fmt, const uint8_t* scalars, uint32_t scalar_fmt,
+                            uint64_t i0, uint64_t n, const XchgArea* area, uint8_t* out, uint32_t* bad) {
+    cudaStream_t s = sl.stream;
+    TRY(sl.stage.ensure(n * 96 + 16));
+    TRY(sl.adhoc.ensure(n * 96 + 16));
+    TRY(sl.scalars.ensure(n * 32 + 16));
+    TRY(sl.out_canon.ensure(96));
+    TRY(sl.flag.ensure(4));
+    TRY(sl.h_out.ensure(128));
+    TRY(ws_enter(sl, s));
+    if (n) {
+        CU(cudaMemcpyAsync(sl.stage.p, g1_affine + 96 * i0, n * 96, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(sl.scalars.p, scalars + 32 * i0, n * 32, cudaMemcpyHostToDevice, s));
+    }
+    CU(cudaMemsetAsync(sl.flag.p, 0, 4, s));
+    if (n)
+        LAUNCH(g1_ingest_kernel, (unsigned)((n + 127) / 128), 128, 0, s, (const uint8_t*)sl.stage.as<uint8_t>(), n, 96u,
+               point_fmt == B200ZK_FMT_MONT ? 1u : 0u, sl.adhoc.as<uint32_t>(), sl.flag.as<uint32_t>());
+    BaseTable t;
+    t.d = sl.adhoc.as<uint32_t>();
+    t.n = n;
+    XchgArgs xa{};
+    if (area) xa = area->args(0);
+    TRY(msm_run(c, sl, &t, t.d, sl.scalars.as<uint32_t>(), n, 1, scalar_fmt, nullptr, area ? nullptr : sl.out_canon.as<uint32_t>(), s, nullptr,
+                nullptr, area ? &xa : nullptr));
+    uint8_t* h = reinterpret_cast<uint8_t*>(sl.h_out.p);
+    if (!area) CU(cudaMemcpyAsync(h, sl.out_canon.p, 96, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h + 96, sl.flag.p, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    memcpy(bad, h + 96, 4);
+    if (!area) memcpy(out, h, 96);
+    return B200ZK_OK;
+}
+
 int32_t b200zk_msm_g1_adhoc(const uint8_t* g1_affine, uint32_t point_fmt, const uint8_t* scalars, uint32_t scalar_fmt,
                             uint64_t n, uint8_t out_affine[96]) {
-    // One pass on the context stream with cached workspaces: no table registration, no allocation, one
-    // synchronisation at the end (the verifier calls this once per proof or per batch).
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(need_init());
+    // One pass per GPU on a slot's stream with cached workspaces: no table registration, no allocation, one synchronisation
+    // at the end (the verifier calls this once per proof or per batch).  A long sum (the 1024-proof batch of
+    // /root/reference/src/circuits/schnorr_circuit.rs:224-229) is split by point range over the bound GPUs, whose partial
+    // sums meet like those of a sharded commitment.
+    Ctx* cp = nullptr;
+    TRY(current_ctx(&cp));
     if (!out_affine || ((!g1_affine || !scalars) && n)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (point_fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown point format");
     if (scalar_fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown scalar format");
     if (n == 0) { memset(out_affine, 0, 96); return B200ZK_OK; }
-    cudaStream_t s = g.stream;
-    TRY(g.stage.ensure(n * 96 + 16));
-    TRY(g.adhoc.ensure(n * 96));
-    TRY(g.scalars.ensure(n * 32 + 16));
-    TRY(g.out_canon.ensure(96));
-    TRY(g.flag.ensure(4));
-    CU(cudaMemcpyAsync(g.stage.p, g1_affine, n * 96, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(g.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(g.flag.p, 0, 4, s));
-    LAUNCH(g1_ingest_kernel, (unsigned)((n + 127) / 128), 128, 0, s, (const uint8_t*)g.stage.as<uint8_t>(), n, 96u,
-           point_fmt == B200ZK_FMT_MONT ? 1u : 0u, g.adhoc.as<uint32_t>(), g.flag.as<uint32_t>());
-    BaseTable t;
-    t.d = g.adhoc.as<uint32_t>();
-    t.n = n;
-    TRY(msm_run(&t, t.d, g.scalars.as<uint32_t>(), n, 1, scalar_fmt, nullptr, g.out_canon.as<uint32_t>(), s));
-    uint32_t bad = 0;
-    CU(cudaMemcpyAsync(out_affine, g.out_canon.p, 96, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(&bad, g.flag.p, 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    if (bad) { memset(out_affine, 0, 96); return fail(B200ZK_ERR_BAD_POINT, "a base point is not a canonical point on the curve"); }
+    const int D = (int)g_devs.size();
+    static uint64_t split_min = 0;
+    if (!split_min) { const char* v = getenv("B200ZK_ADHOC_SPLIT_MIN"); split_min = v ? (uint64_t)atoll(v) : 8192; if (!split_min) split_min = 1; }
+    int32_t rc;
+    uint32_t any_bad = 0;
+    if (D == 1 || n < split_min) {
+        DeviceScope ds(cp->ordinal);
+        SlotLease lease(*cp);
+        rc = adhoc_device(*cp, *lease.s, g1_affine, point_fmt, scalars, scalar_fmt, 0, n, nullptr, out_affine, &any_bad);
+    } else {
+        std::vector<SlotLease> leases;
+        for (auto& c : g_devs) leases.emplace_back(*c);
+        XchgArea* area = acquire_area();
+        area->seq++;
+        area->n_parts = (uint32_t)D;
+        std::vector<XchgArea> views(D);
+        std::vector<uint32_t> bad(D, 0);
+        std::vector<Job> jobs;
+        for (int k = 0; k < D; k++) {
+            views[k].base = area->base;
+            views[k].host_canon = area->host_canon;
+            views[k].n_parts = area->n_parts;
+            views[k].part = (uint32_t)k;
+            views[k].seq = area->seq;
+            uint64_t lo = n * k / D, hi = n * (k + 1) / D;
+            Ctx* c = g_devs[k].get();
+            Slot* sl = leases[k].s;
+            XchgArea* view = &views[k];
+            uint32_t* b = &bad[k];
+            jobs.push_back({c, [=]() -> int32_t {
+                                return adhoc_device(*c, *sl, g1_affine, point_fmt, scalars, scalar_fmt, lo, hi - lo, view, nullptr, b);
+                            }});
+        }
+        rc = run_jobs(jobs);
+        if (rc == B200ZK_OK) memcpy(out_affine, area->host_canon, 96);
+        release_area(area);
+        for (uint32_t b : bad) any_bad |= b;
+    }
+    if (rc != B200ZK_OK) return rc;
+    if (any_bad) { memset(out_affine, 0, 96); return fail(B200ZK_ERR_BAD_POINT, "a base point is not a canonical point on the curve"); }
     return B200ZK_OK;
+}
+
+// the device a "_dev" MSM runs on is the one that owns the scalars; the table must have the slice resident there
+static int32_t msm_dev_common(uint64_t bases, uint64_t offset, const void* d_scalars, uint64_t n, uint32_t batch, uint32_t scalar_fmt,
+                              void* d_out_mont, void* d_out_canon, void* d_out_xyzz, void* stream, const XchgArgs* xa) {
+    if (scalar_fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown scalar format");
+    if (((uintptr_t)d_scalars | (uintptr_t)d_out_mont | (uintptr_t)d_out_canon | (uintptr_t)d_out_xyzz) & 15)
+        return fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
+    Ctx* cp = nullptr;
+    const void* hint = d_scalars ? d_scalars : (d_out_mont ? d_out_mont : (d_out_canon ? d_out_canon : d_out_xyzz));
+    TRY(ctx_for_pointer(hint, &cp));
+    std::shared_ptr<TableSet> ts;
+    TRY(get_table(bases, offset, n, &ts));
+    const TableShard* sh = shard_on(*ts, cp->index, offset, n);
+    if (!sh) return fail(B200ZK_ERR_INVALID_ARG, "msm: this slice of the table is not resident on the GPU that owns the scalars");
+    DeviceScope ds(cp->ordinal);
+    SlotLease lease(*cp);
+    return msm_run(*cp, *lease.s, &sh->t, sh->t.d + 24 * (offset - sh->start), reinterpret_cast<const uint32_t*>(d_scalars), n, batch,
+                   scalar_fmt, reinterpret_cast<uint32_t*>(d_out_mont), reinterpret_cast<uint32_t*>(d_out_canon),
+                   reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<uint32_t*>(d_out_xyzz), nullptr, xa);
 }
 
 int32_t b200zk_msm_g1_dev(uint64_t bases, uint64_t offset, const void* d_scalars, uint64_t n, uint32_t batch,
                           uint32_t scalar_fmt, void* d_out_mont, void* d_out_canon, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     TRY(need_init());
     if ((!d_scalars && n && batch) || (!d_out_mont && !d_out_canon)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
-    if (scalar_fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown scalar format");
-    if (((uintptr_t)d_scalars | (uintptr_t)d_out_mont | (uintptr_t)d_out_canon) & 15)
-        return fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
-    const uint32_t* d_bases = nullptr;
-    const BaseTable* tab = nullptr;
-    TRY(lookup_bases(bases, offset, n, &d_bases, &tab));
-    return msm_run(tab, d_bases, reinterpret_cast<const uint32_t*>(d_scalars), n, batch, scalar_fmt,
-                   reinterpret_cast<uint32_t*>(d_out_mont), reinterpret_cast<uint32_t*>(d_out_canon),
-                   reinterpret_cast<cudaStream_t>(stream));
+    return msm_dev_common(bases, offset, d_scalars, n, batch, scalar_fmt, d_out_mont, d_out_canon, nullptr, stream, nullptr);
 }
 
 int32_t b200zk_msm_g1_partial_dev(uint64_t bases, uint64_t offset, const void* d_scalars, uint64_t n, uint32_t scalar_fmt,
                                   void* d_out_xyzz, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     TRY(need_init());
     if ((!d_scalars && n) || !d_out_xyzz) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
-    if (scalar_fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown scalar format");
-    if (((uintptr_t)d_scalars | (uintptr_t)d_out_xyzz) & 15) return fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
-    const uint32_t* d_bases = nullptr;
-    const BaseTable* tab = nullptr;
-    TRY(lookup_bases(bases, offset, n, &d_bases, &tab));
-    if (n == 0) { CU(cudaMemsetAsync(d_out_xyzz, 0, 192, reinterpret_cast<cudaStream_t>(stream))); return B200ZK_OK; }
-    return msm_run(tab, d_bases, reinterpret_cast<const uint32_t*>(d_scalars), n, 1, scalar_fmt, nullptr, nullptr,
-                   reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<uint32_t*>(d_out_xyzz));
+    return msm_dev_common(bases, offset, d_scalars, n, 1, scalar_fmt, nullptr, nullptr, d_out_xyzz, stream, nullptr);
 }
 
 int32_t b200zk_g1_sum_partials_dev(const void* d_partials_xyzz, uint32_t n, void* d_out_mont, void* d_out_canon, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(need_init());
+    Ctx* c = nullptr;
+    TRY(ctx_for_pointer(d_partials_xyzz, &c));
     if ((!d_partials_xyzz && n) || (!d_out_mont && !d_out_canon)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    DeviceScope ds(c->ordinal);
     LAUNCH(g1_sum_xyzz_kernel, 1, 32, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const uint32_t*>(d_partials_xyzz),
            n, reinterpret_cast<uint32_t*>(d_out_mont), reinterpret_cast<uint32_t*>(d_out_canon));
     return B200ZK_OK;
 }
 
 int32_t b200zk_g1_sum_dev(const void* d_points_mont, uint32_t n, void* d_out_mont, void* d_out_canon, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(need_init());
+    Ctx* c = nullptr;
+    TRY(ctx_for_pointer(d_points_mont, &c));
     if ((!d_points_mont && n) || (!d_out_mont && !d_out_canon)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    DeviceScope ds(c->ordinal);
     LAUNCH(g1_sum_kernel, 1, 32, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const uint32_t*>(d_points_mont), n,
            reinterpret_cast<uint32_t*>(d_out_mont), reinterpret_cast<uint32_t*>(d_out_canon));
     return B200ZK_OK;
 }
 
+// ---- exchange between processes (one process per GPU) ------------------------------------------
+int32_t b200zk_xchg_create(uint32_t n_parts, uint8_t out_ipc_handle[64], uint64_t* out_xchg) {
+    Ctx* c = nullptr;
+    TRY(current_ctx(&c));
+    if (!out_ipc_handle || !out_xchg) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    if (n_parts < 1 || n_parts > XCHG_MAX_PARTS) return fail(B200ZK_ERR_INVALID_ARG, "an exchange has 1..16 parts");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceScope ds(c->ordinal);
+    auto a = std::make_unique<XchgArea>();
+    CU(cudaMalloc(&a->base, XchgArea::bytes()));
+    CU(cudaMemset(a->base, 0, XchgArea::bytes()));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, a->base));
+    memcpy(out_ipc_handle, &h, 64);
+    a->n_parts = n_parts;
+    a->part = 0;
+    a->owner = true;
+    a->home_ordinal = c->ordinal;
+    std::lock_guard<std::mutex> lk(g_area_mu);
+    *out_xchg = g_next_xchg++;
+    g_xchg[*out_xchg] = std::move(a);
+    return B200ZK_OK;
+}
+
+int32_t b200zk_xchg_open(const uint8_t ipc_handle[64], uint32_t n_parts, uint32_t part, uint64_t* out_xchg) {
+    Ctx* c = nullptr;
+    TRY(current_ctx(&c));
+    if (!ipc_handle || !out_xchg) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    if (n_parts < 1 || n_parts > XCHG_MAX_PARTS || part >= n_parts) return fail(B200ZK_ERR_INVALID_ARG, "bad part index");
+    DeviceScope ds(c->ordinal);
+    auto a = std::make_unique<XchgArea>();
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, 64);
+    CU(cudaIpcOpenMemHandle((void**)&a->base, h, cudaIpcMemLazyEnablePeerAccess));
+    a->n_parts = n_parts;
+    a->part = part;
+    a->ipc = true;
+    a->home_ordinal = c->ordinal;
+    std::lock_guard<std::mutex> lk(g_area_mu);
+    *out_xchg = g_next_xchg++;
+    g_xchg[*out_xchg] = std::move(a);
+    return B200ZK_OK;
+}
+
+int32_t b200zk_xchg_close(uint64_t xchg) {
+    TRY(need_init());
+    std::unique_ptr<XchgArea> a;
+    {
+        std::lock_guard<std::mutex> lk(g_area_mu);
+        auto it = g_xchg.find(xchg);
+        if (it == g_xchg.end()) return fail(B200ZK_ERR_BAD_HANDLE, "unknown exchange handle");
+        a = std::move(it->second);
+        g_xchg.erase(it);
+    }
+    DeviceScope ds(a->home_ordinal);
+    CU(cudaDeviceSynchronize());
+    if (a->ipc) CU(cudaIpcCloseMemHandle(a->base));
+    else CU(cudaFree(a->base));
+    a->status.release();
+    return B200ZK_OK;
+}
+
+int32_t b200zk_msm_g1_xchg_dev(uint64_t bases, uint64_t offset, const void* d_scalars, uint64_t n, uint32_t scalar_fmt, uint64_t xchg,
+                               void* d_out_mont, void* d_out_canon, void* stream) {
+    TRY(need_init());
+    if ((!d_scalars && n) || (!d_out_mont && !d_out_canon)) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    XchgArea* a = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_area_mu);
+        auto it = g_xchg.find(xchg);
+        if (it == g_xchg.end()) return fail(B200ZK_ERR_BAD_HANDLE, "unknown exchange handle");
+        a = it->second.get();
+    }
+    // every part calls this the same number of times, so the sequence numbers agree without communication
+    a->seq++;
+    XchgArgs xa = a->args(0);
+    Ctx* cp = nullptr;
+    TRY(ctx_for_pointer(d_out_mont ? d_out_mont : d_out_canon, &cp));
+    DeviceScope ds(cp->ordinal);
+    TRY(a->status.ensure(16));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (a->seq == 1) CU(cudaMemsetAsync(a->status.p, 0, 16, s));
+    if (n == 0) {
+        LAUNCH(msm_combine_kernel, 1, 32, 0, s, (const uint32_t*)nullptr, 0u, 0u, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, xa);
+    } else {
+        TRY(msm_dev_common(bases, offset, d_scalars, n, 1, scalar_fmt, nullptr, nullptr, nullptr, stream, &xa));
+    }
+    // wait (bounded: ~4 s of SM clock) for the last arriver's result and bring it into local HBM
+    LAUNCH(xchg_fetch_kernel, 1, 32, 0, s, (const unsigned long long*)xa.done, xa.seq, (const uint32_t*)xa.res_mont, (const uint32_t*)xa.res_canon,
+           reinterpret_cast<uint32_t*>(d_out_mont), reinterpret_cast<uint32_t*>(d_out_canon), a->status.as<uint32_t>(), 8000000000ll);
+    return B200ZK_OK;
+}
+
+int32_t b200zk_msm_g1_xchg(uint64_t bases, uint64_t offset, const uint8_t* scalars, uint64_t n, uint32_t scalar_fmt, uint64_t xchg,
+                           uint8_t out_affine[96]) {
+    Ctx* cp = nullptr;
+    TRY(current_ctx(&cp));
+    if ((!scalars && n) || !out_affine) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    if (scalar_fmt > B200ZK_FMT_MONT) return fail(B200ZK_ERR_INVALID_ARG, "unknown scalar format");
+    XchgArea* a = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_area_mu);
+        auto it = g_xchg.find(xchg);
+        if (it == g_xchg.end()) return fail(B200ZK_ERR_BAD_HANDLE, "unknown exchange handle");
+        a = it->second.get();
+    }
+    std::shared_ptr<TableSet> ts;
+    TRY(get_table(bases, offset, n, &ts));
+    const TableShard* sh = shard_on(*ts, cp->index, offset, n);
+    if (!sh) return fail(B200ZK_ERR_INVALID_ARG, "msm: this slice of the table is not resident on the selected GPU");
+    a->seq++;
+    XchgArea view = *a;
+    view.status = DevBuf();
+    view.fetch = true;
+    ColSrc src;
+    src.base = scalars;
+    src.stride = (size_t)n * 32;
+    DeviceScope ds(cp->ordinal);
+    SlotLease lease(*cp);
+    // (the scalars stream up in two pieces under the first piece's accumulation, like the single-GPU call)
+    return msm_host_device(*cp, *lease.s, &sh->t, offset - sh->start, src, 0, 1, 0, n, scalar_fmt, &view, out_affine);
+}
+
+int32_t b200zk_xchg_status(uint64_t xchg, uint32_t* out_timed_out) {
+    TRY(need_init());
+    if (!out_timed_out) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    XchgArea* a = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_area_mu);
+        auto it = g_xchg.find(xchg);
+        if (it == g_xchg.end()) return fail(B200ZK_ERR_BAD_HANDLE, "unknown exchange handle");
+        a = it->second.get();
+    }
+    *out_timed_out = 0;
+    if (!a->status.p) return B200ZK_OK;
+    DeviceScope ds(a->home_ordinal);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out_timed_out, a->status.p, 4, cudaMemcpyDeviceToHost));
+    return B200ZK_OK;
+}
+
 int32_t b200zk_ntt_fr_dev(void* d_data, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
                           const uint8_t coset_shift[32], void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     TRY(need_init());
     if (!d_data || !omega) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if ((uintptr_t)d_data & 15) return fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
-    return ntt_run(reinterpret_cast<uint32_t*>(d_data), batch, log_n, omega, flags, coset_shift,
+    Ctx* c = nullptr;
+    TRY(ctx_for_pointer(d_data, &c));
+    DeviceScope ds(c->ordinal);
+    SlotLease lease(*c);
+    return ntt_run(*c, *lease.s, reinterpret_cast<uint32_t*>(d_data), batch, log_n, omega, flags, coset_shift,
                    reinterpret_cast<cudaStream_t>(stream));
 }
 
 int32_t b200zk_ntt_fr_batch(uint8_t* data, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
                             const uint8_t coset_shift[32]) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(need_init());
-    if (!data || !omega) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
-    if (log_n > 32) return fail(B200ZK_ERR_INVALID_ARG, "ntt: log_n exceeds the 2-adicity of Fr");
-    if (batch == 0) return B200ZK_OK;
-    size_t bytes = ((size_t)batch << log_n) * 32;
-    TRY(g.ntt_data.ensure(bytes));
-    static int64_t pipe_min = -1;   // batches with at least this many bytes are pipelined group by group
-    if (pipe_min < 0) { const char* v = getenv("B200ZK_NTT_PIPE_MIN_BYTES"); pipe_min = v ? atoll(v) : (32ll << 20); }
-    if (batch >= 4 && pipe_min > 0 && bytes >= (size_t)pipe_min) {
-        // A transform is PCIe-bound end to end (2^22: 2.4 ms up, 0.94 ms of kernels, 2.4 ms down), and the link is full
-        // duplex: group g+1 goes up and group g-1 comes down while group g is transformed.
-        if (!g.copy_stream) {
-            CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&g.copy_ev[0], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&g.copy_ev[1], cudaEventDisableTiming));
-        }
-        if (!g.down_stream) CU(cudaStreamCreateWithFlags(&g.down_stream, cudaStreamNonBlocking));
-        const uint32_t groups = std::min<uint32_t>(8, batch / 2);
-        const size_t poly = ((size_t)1 << log_n) * 32;
-        std::vector<cudaEvent_t>& up = g.pipe_up;
-        std::vector<cudaEvent_t>& done = g.pipe_done;
-        while (up.size() < groups) {
-            cudaEvent_t e1, e2;
-            CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-            up.push_back(e1);
-            done.push_back(e2);
-        }
-        uint8_t* d = g.ntt_data.as<uint8_t>();
-        for (uint32_t k = 0; k < groups; k++) {
-            const uint32_t b0 = (uint32_t)((uint64_t)batch * k / groups), b1 = (uint32_t)((uint64_t)batch * (k + 1) / groups);
-            const size_t off = b0 * poly, len = (size_t)(b1 - b0) * poly;
-            CU(cudaMemcpyAsync(d + off, data + off, len, cudaMemcpyHostToDevice, g.copy_stream));
-            CU(cudaEventRecord(up[k], g.copy_stream));
-            CU(cudaStreamWaitEvent(g.stream, up[k], 0));
-            TRY(ntt_run(reinterpret_cast<uint32_t*>(d + off), b1 - b0, log_n, omega, flags, coset_shift, g.stream));
-            CU(cudaEventRecord(done[k], g.stream));
-            CU(cudaStreamWaitEvent(g.down_stream, done[k], 0));
-            CU(cudaMemcpyAsync(data + off, d + off, len, cudaMemcpyDeviceToHost, g.down_stream));
-        }
-        CU(cudaStreamSynchronize(g.down_stream));
-        CU(cudaStreamSynchronize(g.stream));
-        return B200ZK_OK;
-    }
-    CU(cudaMemcpyAsync(g.ntt_data.p, data, bytes, cudaMemcpyHostToDevice, g.stream));
-    TRY(ntt_run(g.ntt_data.as<uint32_t>(), batch, log_n, omega, flags, coset_shift, g.stream));
-    CU(cudaMemcpyAsync(data, g.ntt_data.p, bytes, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
-    return B200ZK_OK;
+    PolySrc src;
+    src.base = data;
+    return ntt_host(src, batch, log_n, omega, flags, coset_shift);
+}
+
+int32_t b200zk_ntt_fr_batch_ptrs(uint8_t* const* data, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
+                                 const uint8_t coset_shift[32]) {
+    if (!data && batch) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    PolySrc src;
+    src.ptrs = data;
+    return ntt_host(src, batch, log_n, omega, flags, coset_shift);
 }
 
 int32_t b200zk_ntt_fr(uint8_t* data, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
@@ -1269,120 +2073,24 @@ int32_t b200zk_g1_compress(const uint8_t affine[96], uint8_t out[48]) {
 }
 
 int32_t b200zk_g1_synth_bases_dev(uint64_t seed, uint64_t start, uint64_t n, void* d_out_mont, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(need_init());
+    Ctx* cp = nullptr;
+    TRY(ctx_for_pointer(d_out_mont, &cp));
     if (!d_out_mont && n) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    Ctx& c = *cp;
+    DeviceScope ds(c.ordinal);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (!g.fixed_table) {
-        uint32_t* d_gen = nullptr;
-        TRY(get_generator_dev(&d_gen, s));
-        CU(cudaMalloc(&g.fixed_table, 8 * 256 * 96));
-        LAUNCH(g1_fixed_table_kernel, 16, 128, 0, s, (const uint32_t*)d_gen, g.fixed_table);
-    }
-    if (n) LAUNCH(g1_synth_bases_kernel, (unsigned)((n + 127) / 128), 128, 0, s, (const uint32_t*)g.fixed_table, seed, start, n,
-                  reinterpret_cast<uint32_t*>(d_out_mont));
-    return B200ZK_OK;
-}
-
-int32_t b200zk_selftest_field(uint32_t field, uint32_t op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint64_t count) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(need_init());
-    if (field > 1 || op > 3 || !a || !out || (op < 3 && !b)) return fail(B200ZK_ERR_INVALID_ARG, "bad selftest arguments");
-    if (count == 0) return B200ZK_OK;
-    size_t esz = field ? 48 : 32, bytes = esz * count;
-    TRY(g.stage.ensure(3 * bytes + 64));
-    uint8_t* da = g.stage.as<uint8_t>();
-    uint8_t* db = da + bytes;
-    uint8_t* dout = db + bytes;
-    CU(cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, g.stream));
-    if (b) CU(cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, g.stream));
-    unsigned grid = (unsigned)((count + 127) / 128);
-    if (field == 0)
-        LAUNCH(selftest_kernel<FrParams>, grid, 128, 0, g.stream, (const uint32_t*)da, b ? (const uint32_t*)db : nullptr,
-               (uint32_t*)dout, count, op);
-    else
-        LAUNCH(selftest_kernel<FpParams>, grid, 128, 0, g.stream, (const uint32_t*)da, b ? (const uint32_t*)db : nullptr,
-               (uint32_t*)dout, count, op);
-    CU(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
-    return B200ZK_OK;
-}
-
-int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double* out_ops_per_s, double* out_ms) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    TRY(need_init());
-    if (kind > 11 || !out_ops_per_s) return fail(B200ZK_ERR_INVALID_ARG, "bad microbench arguments");
-    int sms = g.prop.multiProcessorCount;
-    unsigned threads = (kind == 3) ? 128 : 256;
-    unsigned blocks = (unsigned)sms * ((kind == 3) ? 3 : ((kind == 2) ? 4 : 8));
-    TRY(g.stage.ensure((size_t)blocks * threads * 8 + 64));
     uint32_t* d_gen = nullptr;
-    if (kind == 3) TRY(get_generator_dev(&d_gen, g.stream));
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    double per_thread = 0;
-    for (int rep = 0; rep < 2; rep++) {  // rep 0 warms up
-        CU(cudaEventRecord(e0, g.stream));
-        switch (kind) {
-            case 0:
-                LAUNCH(mb_imad_wide_kernel, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
-                per_thread = 32.0 * iters;
-                break;
-            case 1:
-                LAUNCH(mb_imad_pair_kernel, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
-                per_thread = 32.0 * iters;
-                break;
-            case 2:
-                LAUNCH(mb_femul_kernel<FpParams>, blocks, threads, 0, g.stream, g.stage.as<uint32_t>(), iters);
-                per_thread = 2.0 * iters;
-                break;
-            case 3:
-                LAUNCH(mb_madd_kernel, blocks, threads, 0, g.stream, (const uint32_t*)d_gen, g.stage.as<uint32_t>(), iters);
-                per_thread = 1.0 * iters;
-                break;
-            case 4:
-                LAUNCH(mb_femul_kernel<FrParams>, blocks, threads, 0, g.stream, g.stage.as<uint32_t>(), iters);
-                per_thread = 2.0 * iters;
-                break;
-            case 5:
-                LAUNCH(mb_imad_chain_kernel, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
-                per_thread = 24.0 * iters;
-                break;
-            case 6:
-                LAUNCH(mb_dfma_kernel, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 1.000001, 0.999999);
-                per_thread = 32.0 * iters;
-                break;
-            case 7:
-                LAUNCH(mb_imad_cout_kernel, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
-                per_thread = 24.0 * iters;
-                break;
-            case 9:
-                LAUNCH(mb_imad_parts_kernel<0>, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
-                per_thread = 32.0 * iters;
-                break;
-            case 10:
-                LAUNCH(mb_imad_parts_kernel<1>, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
-                per_thread = 32.0 * iters;
-                break;
-            case 11:
-                LAUNCH(mb_imad_parts_kernel<2>, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
-                per_thread = 32.0 * iters;
-                break;
-            default:
-                LAUNCH(mb_imad_alu_kernel, blocks, threads, 0, g.stream, g.stage.as<uint64_t>(), iters, 12345u, 67890u);
-                per_thread = 32.0 * iters;
-                break;
+    TRY(get_generator_dev(c, &d_gen, s));
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (!c.fixed_table) {
+            CU(cudaMalloc(&c.fixed_table, 8 * 256 * 96));
+            LAUNCH(g1_fixed_table_kernel, 16, 128, 0, c.stream, (const uint32_t*)d_gen, c.fixed_table);
+            CU(cudaStreamSynchronize(c.stream));
         }
-        CU(cudaEventRecord(e1, g.stream));
-        CU(cudaEventSynchronize(e1));
     }
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    *out_ops_per_s = per_thread * (double)blocks * threads / (ms * 1e-3);
-    if (out_ms) *out_ms = ms;
+    if (n) LAUNCH(g1_synth_bases_kernel, (unsigned)((n + 127) / 128), 128, 0, s, (const uint32_t*)c.fixed_table, seed, start, n,
+                  reinterpret_cast<uint32_t*>(d_out_mont));
     return B200ZK_OK;
 }
 
@@ -1390,25 +2098,37 @@ uint64_t b200zk_launch_count(void) { return g_launches.load(); }
 
 int32_t b200zk_set_profiling(uint32_t enable) {
     std::lock_guard<std::mutex> lk(g_mu);
-    g.profiling = enable != 0;
-    g.ev_count = 0;
+    g_profiling = enable != 0;
+    g_prof_ctx = nullptr;
+    g_prof_slot = nullptr;
     return B200ZK_OK;
 }
 
 int32_t b200zk_get_profile(uint32_t* kind, double* phase_ms, uint32_t cap, uint32_t* n_phases, uint32_t* msm_window_bits,
                            uint32_t* msm_windows) {
-    std::lock_guard<std::mutex> lk(g_mu);
     TRY(need_init());
     if (!kind || !phase_ms || !n_phases) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
-    *kind = (uint32_t)g.ev_kind;
+    Ctx* c;
+    Slot* sl;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        c = g_prof_ctx;
+        sl = g_prof_slot;
+    }
+    *kind = 0;
     *n_phases = 0;
-    if (msm_window_bits) *msm_window_bits = g.last_plan.c;
-    if (msm_windows) *msm_windows = g.last_plan.W;
-    if (g.ev_count < 2) return B200ZK_OK;
-    CU(cudaEventSynchronize(g.ev[g.ev_count - 1]));
-    for (int i = 0; i + 1 < g.ev_count && (uint32_t)i < cap; i++) {
+    if (msm_window_bits) *msm_window_bits = 0;
+    if (msm_windows) *msm_windows = 0;
+    if (!c || !sl) return B200ZK_OK;
+    *kind = (uint32_t)sl->ev_kind;
+    if (msm_window_bits) *msm_window_bits = sl->last_plan.c;
+    if (msm_windows) *msm_windows = sl->last_plan.W;
+    if (sl->ev_count < 2) return B200ZK_OK;
+    DeviceScope ds(c->ordinal);
+    CU(cudaEventSynchronize(sl->ev[sl->ev_count - 1]));
+    for (int i = 0; i + 1 < sl->ev_count && (uint32_t)i < cap; i++) {
         float ms = 0;
-        CU(cudaEventElapsedTime(&ms, g.ev[i], g.ev[i + 1]));
+        CU(cudaEventElapsedTime(&ms, sl->ev[i], sl->ev[i + 1]));
         phase_ms[i] = ms;
         *n_phases = (uint32_t)i + 1;
     }
@@ -1417,10 +2137,10 @@ int32_t b200zk_get_profile(uint32_t* kind, double* phase_ms, uint32_t cap, uint3
 
 int32_t b200zk_set_msm_tuning(uint32_t window_bits, uint32_t smax) {
     std::lock_guard<std::mutex> lk(g_mu);
-    g.tune_c = window_bits & 0xffu;
-    g.tune_variant = ((window_bits >> 8) & 0x7fu) ? ((window_bits >> 8) & 0x7fu) - 1 : 6;  // bits 8..14: 1 + accumulate-kernel variant
-    g.tune_no_tables = (window_bits >> 15) & 1u;    // bit 15: do not build window tables at registration
-    g.tune_smax = smax;
+    g_tune_c = window_bits & 0xffu;
+    g_tune_variant = ((window_bits >> 8) & 0x7fu) ? ((window_bits >> 8) & 0x7fu) - 1 : 6;  // bits 8..14: 1 + accumulate-kernel variant
+    g_tune_no_tables = (window_bits >> 15) & 1u;    // bit 15: do not build window tables at registration
+    g_tune_smax = smax;
     return B200ZK_OK;
 }
 

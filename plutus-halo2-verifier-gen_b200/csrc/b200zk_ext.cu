@@ -43,40 +43,78 @@ struct GateProgram {
     uint32_t n_instr = 0, n_consts = 0, n_rot = 0, n_columns = 0, log_ext = 0, log_period = 0;
 };
 
-struct Ext {
-    bool hooked = false;
+struct Ext {   // per bound device
+    int ordinal = -1;
     Buf scratch, totals, stage, small, colptr, omega_pows, status;
     size_t small_off = 0, colptr_off = 0;
     uint32_t* fixed_table = nullptr;   // 32 x 256 multiples of G
     std::map<uint64_t, GateProgram> programs;
     uint64_t next_program = 1;
 };
-Ext x;
+Ext g_ext[16];
+bool g_hooked = false;
+std::mutex g_hook_mu;
 
 void ext_shutdown() {
-    Buf* all[] = {&x.scratch, &x.totals, &x.stage, &x.small, &x.colptr, &x.omega_pows, &x.status};
-    for (Buf* b : all) b->release();
-    if (x.fixed_table) { cudaFree(x.fixed_table); x.fixed_table = nullptr; }
-    for (auto& kv : x.programs) {
-        cudaFree(kv.second.program);
-        cudaFree(kv.second.consts);
-        cudaFree(kv.second.rotations);
-        if (kv.second.t_inv) cudaFree(kv.second.t_inv);
+    for (Ext& x : g_ext) {
+        if (x.ordinal < 0) continue;
+        ctx::DeviceScope ds(x.ordinal);
+        Buf* all[] = {&x.scratch, &x.totals, &x.stage, &x.small, &x.colptr, &x.omega_pows, &x.status};
+        for (Buf* b : all) b->release();
+        if (x.fixed_table) { cudaFree(x.fixed_table); x.fixed_table = nullptr; }
+        for (auto& kv : x.programs) {
+            cudaFree(kv.second.program);
+            cudaFree(kv.second.consts);
+            cudaFree(kv.second.rotations);
+            if (kv.second.t_inv) cudaFree(kv.second.t_inv);
+        }
+        x.programs.clear();
+        x.small_off = 0;
+        x.colptr_off = 0;
+        x.ordinal = -1;
     }
-    x.programs.clear();
-    x.small_off = 0;
-    x.colptr_off = 0;
 }
 
-int32_t enter() {
-    XTRY(ctx::need_init());
-    if (!x.hooked) { ctx::on_shutdown(ext_shutdown); x.hooked = true; }
-    return B200ZK_OK;
-}
+// One entry-point invocation: binds the device (the owner of `hint`, else the calling thread's selected device), makes it
+// current, takes the device mutex (the scratch buffers and rings below are shared by every caller of that device) and
+// restores the caller's CUDA device on exit.
+struct Call {
+    ctx::Dev* d = nullptr;
+    Ext* x = nullptr;
+    int prev = -1;
+    std::unique_lock<std::mutex> lk;
+    int32_t begin(const void* hint = nullptr) {
+        XTRY(hint ? ctx::for_pointer(hint, &d) : ctx::current(&d));
+        return begin_bound();
+    }
+    int32_t begin_bound() {
+        {
+            std::lock_guard<std::mutex> hl(g_hook_mu);
+            if (!g_hooked) { ctx::on_shutdown(ext_shutdown); g_hooked = true; }
+        }
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != ctx::ordinal(d)) XCU(cudaSetDevice(ctx::ordinal(d)));
+        else prev = -1;
+        lk = std::unique_lock<std::mutex>(ctx::mutex(d));
+        x = &g_ext[ctx::index(d)];
+        x->ordinal = ctx::ordinal(d);
+        return B200ZK_OK;
+    }
+    // gate-program handles carry the index of the device they were created on
+    int32_t begin_handle(uint64_t handle) {
+        XTRY(ctx::by_index((int)(handle >> 48) - 1, &d));
+        return begin_bound();
+    }
+    cudaStream_t stream() const { return ctx::stream(d); }
+    ~Call() {
+        if (lk.owns_lock()) lk.unlock();
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 
 // `count` canonical Fr values from the host -> Montgomery form in a small device ring; stream-ordered
 constexpr size_t SMALL_BYTES = 1 << 20;
-int32_t upload_fr(const uint8_t* v, uint32_t count, cudaStream_t s, uint32_t** out) {
+int32_t upload_fr(Ext& x, const uint8_t* v, uint32_t count, cudaStream_t s, uint32_t** out) {
     size_t bytes = (size_t)count * 32;
     if (bytes > SMALL_BYTES / 2) return ctx::fail(B200ZK_ERR_INVALID_ARG, "too many host scalars in one call");
     XTRY(x.small.ensure(SMALL_BYTES));
@@ -91,15 +129,17 @@ int32_t upload_fr(const uint8_t* v, uint32_t count, cudaStream_t s, uint32_t** o
 
 // brackets an entry point's use of the shared scratch buffers / scalar ring (ctx.hpp)
 struct WsGuard {
+    ctx::Dev* d = nullptr;
     cudaStream_t s;
     bool active = false;
-    int32_t enter(cudaStream_t st) {
+    int32_t enter(ctx::Dev* dev, cudaStream_t st) {
+        d = dev;
         s = st;
-        int32_t rc = ctx::ws_enter(st);
+        int32_t rc = ctx::ws_enter(dev, st);
         active = rc == B200ZK_OK;
         return rc;
     }
-    ~WsGuard() { if (active) ctx::ws_leave(s); }
+    ~WsGuard() { if (active) ctx::ws_leave(d, s); }
 };
 
 bool misaligned(const void* a, const void* b = nullptr, const void* c = nullptr, const void* d = nullptr) {
@@ -108,16 +148,16 @@ bool misaligned(const void* a, const void* b = nullptr, const void* c = nullptr,
 inline cudaStream_t S(void* stream) { return reinterpret_cast<cudaStream_t>(stream); }
 inline unsigned blocks(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
 
-int32_t fixed_table(cudaStream_t s) {
+int32_t fixed_table(ctx::Dev* d, Ext& x, cudaStream_t s) {
     if (x.fixed_table) return B200ZK_OK;
     uint32_t* d_gen = nullptr;
-    XTRY(ctx::generator_dev(&d_gen, s));
+    XTRY(ctx::generator_dev(d, &d_gen, s));
     XCU(cudaMalloc(&x.fixed_table, (size_t)FIXED_WINDOWS * 256 * 96));
     XLAUNCH(g1_fixed_table32_kernel, FIXED_WINDOWS * 256 / 128, 128, 0, s, (const uint32_t*)d_gen, x.fixed_table);
     return B200ZK_OK;
 }
 
-int32_t batch_invert(const uint32_t* in, uint32_t* out, uint64_t n, cudaStream_t s) {
+int32_t batch_invert(Ext& x, const uint32_t* in, uint32_t* out, uint64_t n, cudaStream_t s) {
     if (n == 0) return B200ZK_OK;
     XTRY(x.scratch.ensure(n * 32));
     XLAUNCH(fr_batch_invert_kernel, blocks(n, BINV_TILE), BINV_THREADS, 0, s, in, out, x.scratch.as<uint32_t>(), n);
@@ -130,36 +170,44 @@ extern "C" {
 
 // ---- device memory for shims that do not link the CUDA runtime ---------------------------------
 int32_t b200zk_dev_alloc(void** out, size_t bytes) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin());
+    Ext& x = *call.x;
+    (void)x;
     if (!out) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null out pointer");
     XCU(cudaMalloc(out, bytes ? bytes : 16));
     return B200ZK_OK;
 }
 int32_t b200zk_dev_free(void* p) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(p));
+    Ext& x = *call.x;
+    (void)x;
     if (p) XCU(cudaFree(p));
     return B200ZK_OK;
 }
 int32_t b200zk_dev_upload(void* d_dst, const void* src, size_t bytes) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_dst));
+    Ext& x = *call.x;
+    (void)x;
     if ((!d_dst || !src) && bytes) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (bytes) {
-        XCU(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, ctx::stream()));
-        XCU(cudaStreamSynchronize(ctx::stream()));
+        XCU(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, call.stream()));
+        XCU(cudaStreamSynchronize(call.stream()));
     }
     return B200ZK_OK;
 }
 int32_t b200zk_dev_download(void* dst, const void* d_src, size_t bytes) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_src));
+    Ext& x = *call.x;
+    (void)x;
     if ((!dst || !d_src) && bytes) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (bytes) {
         XCU(cudaDeviceSynchronize());   // the source may have been produced on a caller's stream
-        XCU(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx::stream()));
-        XCU(cudaStreamSynchronize(ctx::stream()));
+        XCU(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, call.stream()));
+        XCU(cudaStreamSynchronize(call.stream()));
     }
     return B200ZK_OK;
 }
@@ -167,8 +215,10 @@ int32_t b200zk_dev_download(void* dst, const void* d_src, size_t bytes) {
 // ---- batched G1 decompression --------------------------------------------------------------------
 int32_t b200zk_g1_decompress_dev(const void* d_compressed, uint64_t n, void* d_out_mont, void* d_out_canon, void* d_status,
                                  void* stream) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_compressed));
+    Ext& x = *call.x;
+    (void)x;
     if (n == 0) return B200ZK_OK;
     if (!d_compressed || !d_status || (!d_out_mont && !d_out_canon)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (misaligned(d_out_mont, d_out_canon)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
@@ -178,11 +228,13 @@ int32_t b200zk_g1_decompress_dev(const void* d_compressed, uint64_t n, void* d_o
 }
 
 int32_t b200zk_g1_decompress_batch(const uint8_t* compressed, uint64_t n, uint8_t* out_affine, uint32_t* status) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin());
+    Ext& x = *call.x;
+    (void)x;
     if (n == 0) return B200ZK_OK;
     if (!compressed || !out_affine) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
-    cudaStream_t s = ctx::stream();
+    cudaStream_t s = call.stream();
     XTRY(x.stage.ensure(n * (48 + 96) + 64));
     XTRY(x.status.ensure(n * 4));
     uint8_t* d_out = x.stage.as<uint8_t>();
@@ -208,15 +260,17 @@ int32_t b200zk_g1_decompress_batch(const uint8_t* compressed, uint64_t n, uint8_
 
 // ---- fixed-base multiplication and SRS generation ------------------------------------------------
 int32_t b200zk_g1_fixed_mul_dev(const void* d_scalars, uint32_t scalar_fmt, uint64_t n, void* d_out_mont, void* stream) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_out_mont));
+    Ext& x = *call.x;
+    (void)x;
     WsGuard ws;
-    XTRY(ws.enter(S(stream)));
+    XTRY(ws.enter(call.d, S(stream)));
     if (n == 0) return B200ZK_OK;
     if (!d_scalars || !d_out_mont) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (scalar_fmt > B200ZK_FMT_MONT) return ctx::fail(B200ZK_ERR_INVALID_ARG, "unknown scalar format");
     if (misaligned(d_scalars, d_out_mont)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
-    XTRY(fixed_table(S(stream)));
+    XTRY(fixed_table(call.d, x, S(stream)));
     XLAUNCH(g1_fixed_mul_kernel, blocks(n, 128), 128, 0, S(stream), (const uint32_t*)x.fixed_table,
             reinterpret_cast<const uint32_t*>(d_scalars), scalar_fmt == B200ZK_FMT_MONT ? 1u : 0u, n, reinterpret_cast<uint32_t*>(d_out_mont));
     return B200ZK_OK;
@@ -224,18 +278,20 @@ int32_t b200zk_g1_fixed_mul_dev(const void* d_scalars, uint32_t scalar_fmt, uint
 
 int32_t b200zk_srs_generate_dev(const uint8_t s_bytes[32], uint32_t k, const uint8_t omega[32], void* d_g_mont,
                                 void* d_g_lagrange_mont, void* stream) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_g_mont ? d_g_mont : d_g_lagrange_mont));
+    Ext& x = *call.x;
+    (void)x;
     WsGuard ws;
-    XTRY(ws.enter(S(stream)));
+    XTRY(ws.enter(call.d, S(stream)));
     if (!s_bytes || (!d_g_mont && !d_g_lagrange_mont) || (d_g_lagrange_mont && !omega)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (k > 28) return ctx::fail(B200ZK_ERR_INVALID_ARG, "srs: k > 28 is not supported");
     if (misaligned(d_g_mont, d_g_lagrange_mont)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
     cudaStream_t st = S(stream);
     const uint64_t n = (uint64_t)1 << k;
-    XTRY(fixed_table(st));
+    XTRY(fixed_table(call.d, x, st));
     uint32_t* d_s = nullptr;
-    XTRY(upload_fr(s_bytes, 1, st, &d_s));
+    XTRY(upload_fr(x, s_bytes, 1, st, &d_s));
     XTRY(x.stage.ensure(n * 32));
     uint32_t* sc = x.stage.as<uint32_t>();
     if (d_g_mont) {   // g[i] = s^i * G
@@ -245,7 +301,7 @@ int32_t b200zk_srs_generate_dev(const uint8_t s_bytes[32], uint32_t k, const uin
     }
     if (d_g_lagrange_mont) {   // g_lagrange[i] = omega^i (s^n - 1) / (n (s - omega^i)) * G
         uint32_t* d_w = nullptr;
-        XTRY(upload_fr(omega, 1, st, &d_w));
+        XTRY(upload_fr(x, omega, 1, st, &d_w));
         XTRY(x.omega_pows.ensure(n * 32));
         XTRY(x.status.ensure(64));
         uint32_t* wp = x.omega_pows.as<uint32_t>();
@@ -253,7 +309,7 @@ int32_t b200zk_srs_generate_dev(const uint8_t s_bytes[32], uint32_t k, const uin
         XCU(cudaMemsetAsync(flag, 0, 4, st));
         XLAUNCH(fr_geometric_kernel, blocks(n, 256 * 8), 256, 0, st, (const uint32_t*)d_w, (const uint32_t*)nullptr, wp, n);
         XLAUNCH(srs_lagrange_pre_kernel, blocks(n, 256), 256, 0, st, (const uint32_t*)wp, (const uint32_t*)d_s, sc, n, flag);
-        XTRY(batch_invert(sc, sc, n, st));
+        XTRY(batch_invert(x, sc, sc, n, st));
         // c = (s^n - 1) / n on the host side of the stream: s^n by k squarings in a one-thread kernel would do,
         // but the geometric kernel already gives s^n as element n of the power series: compute it as 2 elements
         uint32_t* d_c = nullptr;   // [s^n - 1, n] -> c
@@ -277,11 +333,13 @@ int32_t b200zk_srs_generate_dev(const uint8_t s_bytes[32], uint32_t k, const uin
 }
 
 int32_t b200zk_g1_export_dev(const void* d_points_mont, uint64_t n, uint8_t* out_affine) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_points_mont));
+    Ext& x = *call.x;
+    (void)x;
     if (n == 0) return B200ZK_OK;
     if (!d_points_mont || !out_affine) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
-    cudaStream_t s = ctx::stream();
+    cudaStream_t s = call.stream();
     XCU(cudaDeviceSynchronize());
     XTRY(x.scratch.ensure(n * 96));
     XLAUNCH(g1_to_canonical_kernel, blocks(n, 128), 128, 0, s, reinterpret_cast<const uint32_t*>(d_points_mont), x.scratch.as<uint32_t>(), n);
@@ -292,8 +350,10 @@ int32_t b200zk_g1_export_dev(const void* d_points_mont, uint64_t n, uint8_t* out
 
 // ---- Fr vectors ----------------------------------------------------------------------------------
 int32_t b200zk_fr_convert_dev(const void* d_in, void* d_out, uint64_t n, uint32_t to_mont, void* stream) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_out));
+    Ext& x = *call.x;
+    (void)x;
     if (n == 0) return B200ZK_OK;
     if (!d_in || !d_out) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (misaligned(d_in, d_out)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
@@ -303,24 +363,28 @@ int32_t b200zk_fr_convert_dev(const void* d_in, void* d_out, uint64_t n, uint32_
 }
 
 int32_t b200zk_fr_power_table_dev(const uint8_t base[32], uint64_t row0, uint64_t rows, uint64_t cols, void* d_out, void* stream) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_out));
+    Ext& x = *call.x;
+    (void)x;
     WsGuard ws;
-    XTRY(ws.enter(S(stream)));
+    XTRY(ws.enter(call.d, S(stream)));
     if (rows == 0 || cols == 0) return B200ZK_OK;
     if (!base || !d_out) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (misaligned(d_out)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
     if (row0 + rows > (1ull << 32) || cols > (1ull << 32)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "power table: exponents exceed 64 bits");
     uint32_t* d_b = nullptr;
-    XTRY(upload_fr(base, 1, S(stream), &d_b));
+    XTRY(upload_fr(x, base, 1, S(stream), &d_b));
     XLAUNCH(fr_power_table_kernel, blocks(rows * cols, 256), 256, 0, S(stream), (const uint32_t*)d_b, row0, rows, cols,
             reinterpret_cast<uint32_t*>(d_out));
     return B200ZK_OK;
 }
 
 int32_t b200zk_fr_extend_dev(const void* d_in, uint64_t n_in, void* d_out, uint64_t n_out, uint32_t batch, void* stream) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_out));
+    Ext& x = *call.x;
+    (void)x;
     if (batch == 0 || n_out == 0) return B200ZK_OK;
     if (!d_in || !d_out) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (n_in > n_out) return ctx::fail(B200ZK_ERR_INVALID_ARG, "extend: n_in exceeds n_out");
@@ -333,26 +397,30 @@ int32_t b200zk_fr_extend_dev(const void* d_in, uint64_t n_in, void* d_out, uint6
 
 int32_t b200zk_fr_pointwise_dev(uint32_t op, const void* d_a, const void* d_b, const uint8_t scalar[32], void* d_out, uint64_t n,
                                 void* stream) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_out));
+    Ext& x = *call.x;
+    (void)x;
     WsGuard ws;
-    XTRY(ws.enter(S(stream)));
+    XTRY(ws.enter(call.d, S(stream)));
     if (op > 4) return ctx::fail(B200ZK_ERR_INVALID_ARG, "pointwise: unknown op");
     if (n == 0) return B200ZK_OK;
     if (!d_a || !d_out || (op != 3 && !d_b) || (op == 3 && !scalar)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (misaligned(d_a, d_b, d_out)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
     uint32_t* d_s = nullptr;
-    if (op == 3) XTRY(upload_fr(scalar, 1, S(stream), &d_s));
+    if (op == 3) XTRY(upload_fr(x, scalar, 1, S(stream), &d_s));
     XLAUNCH(fr_pointwise_kernel, blocks(n, 256), 256, 0, S(stream), op, reinterpret_cast<const uint32_t*>(d_a),
             reinterpret_cast<const uint32_t*>(d_b), (const uint32_t*)d_s, reinterpret_cast<uint32_t*>(d_out), n);
     return B200ZK_OK;
 }
 
 int32_t b200zk_fr_lincomb_dev(const void* const* d_polys, const uint8_t* coeffs, uint32_t count, void* d_out, uint64_t n, void* stream) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_out));
+    Ext& x = *call.x;
+    (void)x;
     WsGuard ws;
-    XTRY(ws.enter(S(stream)));
+    XTRY(ws.enter(call.d, S(stream)));
     if (!d_out && n) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (n == 0) return B200ZK_OK;
     if (count == 0) { XCU(cudaMemsetAsync(d_out, 0, n * 32, S(stream))); return B200ZK_OK; }
@@ -368,29 +436,33 @@ int32_t b200zk_fr_lincomb_dev(const void* const* d_polys, const uint8_t* coeffs,
             a.poly[j] = reinterpret_cast<const uint32_t*>(d_polys[done + j]);
         }
         uint32_t* d_c = nullptr;
-        XTRY(upload_fr(coeffs + 32 * (size_t)done, a.count, S(stream), &d_c));
+        XTRY(upload_fr(x, coeffs + 32 * (size_t)done, a.count, S(stream), &d_c));
         XLAUNCH(fr_lincomb_kernel, blocks(n, 256), 256, 0, S(stream), a, (const uint32_t*)d_c, reinterpret_cast<uint32_t*>(d_out), n);
     }
     return B200ZK_OK;
 }
 
 int32_t b200zk_fr_batch_invert_dev(const void* d_in, void* d_out, uint64_t n, void* stream) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_out));
+    Ext& x = *call.x;
+    (void)x;
     WsGuard ws;
-    XTRY(ws.enter(S(stream)));
+    XTRY(ws.enter(call.d, S(stream)));
     if (n == 0) return B200ZK_OK;
     if (!d_in || !d_out) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (misaligned(d_in, d_out)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
-    return batch_invert(reinterpret_cast<const uint32_t*>(d_in), reinterpret_cast<uint32_t*>(d_out), n, S(stream));
+    return batch_invert(x, reinterpret_cast<const uint32_t*>(d_in), reinterpret_cast<uint32_t*>(d_out), n, S(stream));
 }
 
 int32_t b200zk_fr_running_product_dev(const void* d_in, void* d_out, uint64_t n, const uint8_t init[32], uint32_t inclusive,
                                       void* stream) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_out));
+    Ext& x = *call.x;
+    (void)x;
     WsGuard ws;
-    XTRY(ws.enter(S(stream)));
+    XTRY(ws.enter(call.d, S(stream)));
     if (n == 0) return B200ZK_OK;
     if (!d_in || !d_out) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (misaligned(d_in, d_out)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
@@ -399,7 +471,7 @@ int32_t b200zk_fr_running_product_dev(const void* d_in, void* d_out, uint64_t n,
     XTRY(x.totals.ensure(tiles * 64));
     uint32_t* tot = x.totals.as<uint32_t>();
     uint32_t* d_init = nullptr;
-    if (init) XTRY(upload_fr(init, 1, s, &d_init));
+    if (init) XTRY(upload_fr(x, init, 1, s, &d_init));
     const uint32_t* in = reinterpret_cast<const uint32_t*>(d_in);
     XLAUNCH(fr_prodscan_totals_kernel, (unsigned)tiles, PS_THREADS, 0, s, in, n, tot);
     XLAUNCH(fr_prodscan_middle_kernel, 1, 256, 0, s, tot, tiles, (const uint32_t*)d_init);
@@ -409,10 +481,12 @@ int32_t b200zk_fr_running_product_dev(const void* d_in, void* d_out, uint64_t n,
 }
 
 int32_t b200zk_fr_kate_div_dev(const void* d_coeffs, uint64_t n, const uint8_t z[32], void* d_quot, void* d_eval, void* stream) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin(d_quot ? d_quot : d_eval));
+    Ext& x = *call.x;
+    (void)x;
     WsGuard ws;
-    XTRY(ws.enter(S(stream)));
+    XTRY(ws.enter(call.d, S(stream)));
     if (!z || (!d_coeffs && n) || (!d_quot && !d_eval)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (misaligned(d_coeffs, d_quot, d_eval)) return ctx::fail(B200ZK_ERR_INVALID_ARG, "device pointers must be 16-byte aligned");
     cudaStream_t s = S(stream);
@@ -425,7 +499,7 @@ int32_t b200zk_fr_kate_div_dev(const void* d_coeffs, uint64_t n, const uint8_t z
     memcpy(zz, z, 32);
     memcpy(zz + 32, z, 32);
     uint32_t* d_z = nullptr;
-    XTRY(upload_fr(zz, 2, s, &d_z));
+    XTRY(upload_fr(x, zz, 2, s, &d_z));
     XLAUNCH(fr_pow_small_kernel, 1, 1, 0, s, d_z + 8, (uint32_t)PS_ITEMS);
     const uint32_t* c = reinterpret_cast<const uint32_t*>(d_coeffs);
     XLAUNCH(fr_horner_totals_kernel, (unsigned)tiles, PS_THREADS, 0, s, c, n, (const uint32_t*)d_z, tot);
@@ -439,8 +513,10 @@ int32_t b200zk_fr_kate_div_dev(const void* d_coeffs, uint64_t n, const uint8_t z
 int32_t b200zk_gate_program_create(const uint32_t* program, uint32_t n_instr, const uint8_t* consts, uint32_t n_consts,
                                    const int32_t* rotations, uint32_t n_rotations, const uint8_t* t_inv, uint32_t log_period,
                                    uint32_t n_columns, uint32_t log_n, uint32_t log_ext, uint64_t* out_handle) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin());
+    Ext& x = *call.x;
+    (void)x;
     if (!out_handle || (!program && n_instr) || (!consts && n_consts) || (!rotations && n_rotations))
         return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer");
     if (log_ext < log_n || log_ext > 32 || n_rotations > 0x1000 || n_columns > 0x10000 || n_consts >= (1u << 28) || log_period > log_ext)
@@ -461,7 +537,7 @@ int32_t b200zk_gate_program_create(const uint32_t* program, uint32_t n_instr, co
         }
         written[dst] = 1;
     }
-    cudaStream_t s = ctx::stream();
+    cudaStream_t s = call.stream();
     GateProgram gp;
     gp.n_instr = n_instr; gp.n_consts = n_consts; gp.n_rot = n_rotations; gp.n_columns = n_columns;
     gp.log_ext = log_ext; gp.log_period = log_period;
@@ -474,7 +550,15 @@ int32_t b200zk_gate_program_create(const uint32_t* program, uint32_t n_instr, co
         XLAUNCH(fr_convert_kernel2, blocks(n_consts, 256), 256, 0, s, (const uint32_t*)gp.consts, gp.consts, (uint64_t)n_consts, 1u);
     }
     std::vector<int32_t> rot(n_rotations);
-    for (uint32_t i = 0; i < n_rotations; i++) rot[i] = rotations[i] * (int32_t)(1u << (log_ext - log_n));
+    for (uint32_t i = 0; i < n_rotations; i++) {
+        // scaled to the extended domain in 64 bits and reduced mod 2^log_ext (a rotation is an index offset on a cyclic domain)
+        int64_t r = (int64_t)rotations[i] * ((int64_t)1 << (log_ext - log_n));
+        int64_t m = (int64_t)1 << log_ext;
+        r %= m;
+        if (r >= m / 2) r -= m;
+        if (r < -(m / 2)) r += m;
+        rot[i] = (int32_t)r;
+    }
     if (n_rotations) XCU(cudaMemcpyAsync(gp.rotations, rot.data(), (size_t)n_rotations * 4, cudaMemcpyHostToDevice, s));
     if (t_inv) {
         uint64_t cnt = (uint64_t)1 << log_period;
@@ -483,19 +567,21 @@ int32_t b200zk_gate_program_create(const uint32_t* program, uint32_t n_instr, co
         XLAUNCH(fr_convert_kernel2, blocks(cnt, 256), 256, 0, s, (const uint32_t*)gp.t_inv, gp.t_inv, cnt, 1u);
     }
     XCU(cudaStreamSynchronize(s));
-    uint64_t h = x.next_program++;
+    uint64_t h = ((uint64_t)(ctx::index(call.d) + 1) << 48) | x.next_program++;
     x.programs[h] = gp;
     *out_handle = h;
     return B200ZK_OK;
 }
 
 int32_t b200zk_gate_program_set_const(uint64_t handle, uint32_t index, const uint8_t value[32]) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin_handle(handle));
+    Ext& x = *call.x;
+    (void)x;
     auto it = x.programs.find(handle);
     if (it == x.programs.end()) return ctx::fail(B200ZK_ERR_BAD_HANDLE, "unknown gate-program handle");
     if (!value || index >= it->second.n_consts) return ctx::fail(B200ZK_ERR_INVALID_ARG, "gate program: constant index out of range");
-    cudaStream_t s = ctx::stream();
+    cudaStream_t s = call.stream();
     uint32_t* d = it->second.consts + 8 * (size_t)index;
     XCU(cudaDeviceSynchronize());
     XCU(cudaMemcpyAsync(d, value, 32, cudaMemcpyHostToDevice, s));
@@ -505,10 +591,12 @@ int32_t b200zk_gate_program_set_const(uint64_t handle, uint32_t index, const uin
 }
 
 int32_t b200zk_gate_program_run_dev(uint64_t handle, const void* const* d_columns, void* d_out, uint32_t accumulate, void* stream) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin_handle(handle));
+    Ext& x = *call.x;
+    (void)x;
     WsGuard ws;
-    XTRY(ws.enter(S(stream)));
+    XTRY(ws.enter(call.d, S(stream)));
     auto it = x.programs.find(handle);
     if (it == x.programs.end()) return ctx::fail(B200ZK_ERR_BAD_HANDLE, "unknown gate-program handle");
     const GateProgram& gp = it->second;
@@ -543,8 +631,10 @@ int32_t b200zk_gate_program_run_dev(uint64_t handle, const void* const* d_column
 }
 
 int32_t b200zk_gate_program_release(uint64_t handle) {
-    std::lock_guard<std::mutex> lk(ctx::mutex());
-    XTRY(enter());
+    Call call;
+    XTRY(call.begin_handle(handle));
+    Ext& x = *call.x;
+    (void)x;
     auto it = x.programs.find(handle);
     if (it == x.programs.end()) return ctx::fail(B200ZK_ERR_BAD_HANDLE, "unknown gate-program handle");
     XCU(cudaDeviceSynchronize());

@@ -686,9 +686,49 @@ __global__ void __launch_bounds__(256) msm_reduce_coop8_kernel(const uint32_t* _
 // ---------------------------------------------------------------------------------------
 // 8. window combine + affine normalisation.  out_mont: 24 limbs Montgomery affine;
 //    out_canon: 24 limbs canonical (the wire format), either may be null.
+//
+//    Point-range sharded MSMs (several GPUs, one partial sum each) finish here too: the exchange is fused into
+//    this kernel.  Every part stores its un-normalised XYZZ partial straight into the gather area on the home
+//    GPU (peer store over NVLink: peer access inside one process, a CUDA-IPC mapping across processes), makes it
+//    visible system-wide and bumps the column's arrival counter with a system-scope atomic; whichever part
+//    arrives last folds the partials, normalises once and writes the result (home HBM, optionally a mapped host
+//    buffer).  No collective library call, no extra launch, nobody waits.
 // ---------------------------------------------------------------------------------------
+constexpr uint32_t XCHG_MAX_COLS = 1024, XCHG_MAX_PARTS = 16;
+struct XchgArgs {
+    uint32_t* gather;               // [col][XCHG_MAX_PARTS][48] on the home GPU
+    unsigned long long* arrive;     // [col] arrivals so far (never reset: a column is complete at multiples of n_parts)
+    unsigned long long* done;       // [col] sequence number of the last completed exchange (read by xchg_fetch_kernel)
+    uint32_t* res_mont;             // [col][24] on the home GPU
+    uint32_t* res_canon;            // [col][24] on the home GPU
+    uint32_t* host_canon;           // [col][24] mapped host memory, or null
+    unsigned long long seq;         // this exchange's sequence number
+    uint32_t n_parts, part, col0;
+};
+__device__ __forceinline__ G1Xyzz xyzz_ld_sys(const uint32_t* arr, uint64_t i) {
+    const uint4* q = reinterpret_cast<const uint4*>(arr + 48 * i);
+    uint32_t v[48];
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        uint4 t = __ldcv(q + k);                          // never served from a stale cache line
+        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+    }
+    G1Xyzz a;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { a.x.l[k] = v[k]; a.y.l[k] = v[12 + k]; a.zz.l[k] = v[24 + k]; a.zzz.l[k] = v[36 + k]; }
+    return a;
+}
+__device__ __forceinline__ void g1_write_affine(const G1Xyzz& acc, uint32_t* out_mont, uint32_t* out_canon, uint32_t* out_canon2) {
+    G1Affine a = xyzz_to_affine_ni(acc);
+    if (out_mont) { fp_st(out_mont, a.x); fp_st(out_mont + 12, a.y); }
+    if (out_canon || out_canon2) {
+        Fp cx = fe_from_mont(a.x), cy = fe_from_mont(a.y);
+        if (out_canon) { fp_st(out_canon, cx); fp_st(out_canon + 12, cy); }
+        if (out_canon2) { fp_st(out_canon2, cx); fp_st(out_canon2 + 12, cy); }
+    }
+}
 __global__ void __launch_bounds__(32) msm_combine_kernel(const uint32_t* __restrict__ win_sums, uint32_t W, uint32_t c,
-                                                         uint32_t* out_mont, uint32_t* out_canon, uint32_t* out_xyzz) {
+                                                         uint32_t* out_mont, uint32_t* out_canon, uint32_t* out_xyzz, XchgArgs xa) {
     const uint32_t b = blockIdx.x;             // one warp per batch item, every lane holds the same accumulator
     G1Xyzz acc;
     xyzz_set_inf(acc);
@@ -697,12 +737,58 @@ __global__ void __launch_bounds__(32) msm_combine_kernel(const uint32_t* __restr
         G1Xyzz s = xyzz_ld(win_sums, (uint64_t)b * W + w);
         warp_xyzz_add(acc, s);
     }
+    if (xa.gather) {
+        const uint32_t col = xa.col0 + b;
+        uint32_t last = 0;
+        if (threadIdx.x == 0) {
+            xyzz_st(xa.gather, (uint64_t)col * XCHG_MAX_PARTS + xa.part, acc);
+            __threadfence_system();
+            unsigned long long old = atomicAdd_system(xa.arrive + col, 1ull);
+            last = ((old + 1) % xa.n_parts == 0) ? 1u : 0u;
+            __threadfence_system();
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) return;
+        xyzz_set_inf(acc);
+        for (uint32_t p = 0; p < xa.n_parts; p++) {
+            G1Xyzz s = xyzz_ld_sys(xa.gather, (uint64_t)col * XCHG_MAX_PARTS + p);
+            warp_xyzz_add(acc, s);
+        }
+        if (threadIdx.x != 0) return;
+        g1_write_affine(acc, xa.res_mont + 24 * col, xa.res_canon + 24 * col, xa.host_canon ? xa.host_canon + 24 * col : nullptr);
+        __threadfence_system();
+        atomicExch_system(xa.done + col, xa.seq);
+        return;
+    }
     if (threadIdx.x != 0) return;
     if (out_xyzz) xyzz_st(out_xyzz, b, acc);               // un-normalised partial (multi-GPU exchange)
     if (!out_mont && !out_canon) return;
-    G1Affine a = xyzz_to_affine_ni(acc);
-    if (out_mont) { fp_st(out_mont + 24 * b, a.x); fp_st(out_mont + 24 * b + 12, a.y); }
-    if (out_canon) { fp_st(out_canon + 24 * b, fe_from_mont(a.x)); fp_st(out_canon + 24 * b + 12, fe_from_mont(a.y)); }
+    g1_write_affine(acc, out_mont ? out_mont + 24 * b : nullptr, out_canon ? out_canon + 24 * b : nullptr, nullptr);
+}
+// Every participant of a multi-process exchange ends its call with this: waits (bounded) until the column's result is
+// complete on the home GPU and copies it into local HBM.  status: 0 ok, 1 timed out (a peer never arrived).
+__global__ void xchg_fetch_kernel(const unsigned long long* done, unsigned long long seq, const uint32_t* res_mont,
+                                  const uint32_t* res_canon, uint32_t* out_mont, uint32_t* out_canon, uint32_t* status,
+                                  long long timeout_cycles) {
+    const uint32_t col = blockIdx.x;
+    __shared__ uint32_t ok;
+    if (threadIdx.x == 0) {
+        long long t0 = clock64();
+        uint32_t good = 0;
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(done + col) : "memory");
+            if (v >= seq) { good = 1; break; }
+            if (clock64() - t0 > timeout_cycles) break;
+            __nanosleep(200);
+        }
+        ok = good;
+        if (!good && status) atomicExch(status, 1u);
+    }
+    __syncthreads();
+    if (!ok || threadIdx.x >= 24) return;
+    if (out_mont) out_mont[24 * col + threadIdx.x] = __ldcv(res_mont + 24 * col + threadIdx.x);
+    if (out_canon) out_canon[24 * col + threadIdx.x] = __ldcv(res_canon + 24 * col + threadIdx.x);
 }
 
 // sum of n XYZZ partial points -> affine: the combine step of the point-range sharded MSM

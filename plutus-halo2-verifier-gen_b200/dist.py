@@ -3,8 +3,10 @@
 MSM is linear in the point set, so rank r keeps the slice [r*n/G, (r+1)*n/G) of the SRS table
 resident, receives the matching slice of the scalars, runs the whole Pippenger pipeline locally
 down to one un-normalised point, and the G partial points (192 bytes each, extended Jacobian) are
-exchanged with one all-gather over NVLink and folded on the device (``b200zk_g1_sum_partials_dev``).  One process per GPU;
-``torch.distributed`` is the plumbing (NCCL on GPUs, gloo in the CPU tests of the host logic).
+stored into rank 0's HBM over NVLink from inside the MSM's last kernel and folded by whichever rank arrives last
+(``b200zk_msm_g1_xchg_dev``).  One process per GPU; ``torch.distributed`` is the plumbing (process group, one 64-byte
+broadcast of the IPC handle; NCCL on GPUs, gloo in the CPU tests of the host logic).  The same sharding driven by ONE
+process over all GPUs is behind the plain C ABI (``b200zk_init_devices`` + ``b200zk_msm_g1``).
 
 Batches of independent polynomials are split by :func:`split_batch` with no collective at all.
 """
@@ -30,33 +32,78 @@ def split_batch(n_items: int, rank: int, world: int) -> List[int]:
 
 
 class ShardedMSM:
-    """One rank's share of a point-range sharded MSM.
+    """One rank's share of a point-range sharded MSM (one process per GPU).
 
-    ``bases_handle`` must hold exactly this rank's slice of the table (see :func:`shard_range`)."""
+    ``bases_handle`` must hold exactly this rank's slice of the table (see :func:`shard_range`).
 
-    def __init__(self, bases_handle: int, n_local: int, rank: int = 0, world: int = 1, group=None):
+    ``exchange="peer"`` (default): the partial sums meet in rank 0's HBM through peer stores issued by the last
+    kernel of every rank's MSM (``b200zk_msm_g1_xchg_dev``; the area is shared with CUDA IPC, its 64-byte handle is
+    broadcast once over ``torch.distributed``); the rank that arrives last folds and normalises, no collective runs on
+    the data path.  ``exchange="nccl"``: the plain all-gather of the 192-byte partials + a fold launch, kept as the
+    comparison baseline."""
+
+    def __init__(self, bases_handle: int, n_local: int, rank: int = 0, world: int = 1, group=None, exchange: str = "peer"):
         import torch
 
         self.torch = torch
         self.h = bases_handle
         self.n_local = n_local
         self.rank, self.world, self.group = rank, world, group
+        self.exchange = exchange if world > 1 else "none"
         self.d_part = torch.zeros(192, dtype=torch.uint8, device="cuda")           # XYZZ partial of this rank
         self.d_all = torch.zeros(192 * world, dtype=torch.uint8, device="cuda")
         self.d_out = torch.zeros(96, dtype=torch.uint8, device="cuda")
         self.d_scalars = None
+        self.copy_stream = None
+        self.xchg = None
+        if self.exchange == "peer":
+            hbuf = torch.zeros(64, dtype=torch.uint8)
+            xh = C.c_uint64(0)
+            if rank == 0:
+                raw = C.create_string_buffer(64)
+                check(lib().b200zk_xchg_create(world, capi.addr(raw), C.byref(xh)))
+                hbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+            dev = hbuf.cuda()
+            torch.distributed.broadcast(dev, src=0, group=group)      # plumbing: 64 bytes, once
+            if rank != 0:
+                raw = bytes(dev.cpu().numpy())
+                check(lib().b200zk_xchg_open(capi.addr(raw), world, rank, C.byref(xh)))
+            self.xchg = xh.value
 
-    def run_device(self, d_scalars, scalar_fmt: int = capi.FMT_CANONICAL):
-        """Scalars already in HBM -> result (canonical affine, 96 bytes) in ``self.d_out``; asynchronous
+    def close(self) -> None:
+        if self.xchg:
+            self.torch.cuda.synchronize()
+            if self.world > 1:
+                self.torch.distributed.barrier(group=self.group)     # nobody unmaps while a peer may still store
+            if self.rank != 0:
+                check(lib().b200zk_xchg_close(self.xchg))
+            if self.world > 1:
+                self.torch.distributed.barrier(group=self.group)
+            if self.rank == 0:
+                check(lib().b200zk_xchg_close(self.xchg))
+            self.xchg = None
+
+    def timed_out(self) -> bool:
+        if not self.xchg:
+            return False
+        v = C.c_uint32(0)
+        check(lib().b200zk_xchg_status(self.xchg, C.byref(v)))
+        return bool(v.value)
+
+    def run_device(self, d_scalars, scalar_fmt: int = capi.FMT_CANONICAL, n: Optional[int] = None, offset: int = 0):
+        """Scalars already in HBM -> result (canonical affine, 96 bytes) in ``self.d_out`` on every rank; asynchronous
         on torch's current stream."""
         torch = self.torch
+        n = self.n_local if n is None else n
         st = torch.cuda.current_stream().cuda_stream
         if self.world == 1:
-            check(lib().b200zk_msm_g1_dev(self.h, 0, d_scalars.data_ptr(), self.n_local, 1, scalar_fmt, 0,
-                                          self.d_out.data_ptr(), st))
+            check(lib().b200zk_msm_g1_dev(self.h, offset, d_scalars.data_ptr(), n, 1, scalar_fmt, 0, self.d_out.data_ptr(), st))
             return self.d_out
-        check(lib().b200zk_msm_g1_partial_dev(self.h, 0, d_scalars.data_ptr(), self.n_local, scalar_fmt,
-                                              self.d_part.data_ptr(), st))
+        if self.exchange == "peer":
+            check(lib().b200zk_msm_g1_xchg_dev(self.h, offset, d_scalars.data_ptr(), n, scalar_fmt, self.xchg, 0,
+                                               self.d_out.data_ptr(), st))
+            return self.d_out
+        check(lib().b200zk_msm_g1_partial_dev(self.h, offset, d_scalars.data_ptr(), n, scalar_fmt, self.d_part.data_ptr(), st))
         torch.distributed.all_gather_into_tensor(self.d_all, self.d_part, group=self.group)
         check(lib().b200zk_g1_sum_partials_dev(self.d_all.data_ptr(), self.world, 0, self.d_out.data_ptr(), st))
         return self.d_out
@@ -65,6 +112,10 @@ class ShardedMSM:
         """End-to-end call with host buffers: H2D of this rank's scalars, MSM, exchange, D2H of the
         96-byte result, synchronised on return."""
         torch = self.torch
+        if self.exchange == "peer":
+            check(lib().b200zk_msm_g1_xchg(self.h, 0, h_scalars_pinned.data_ptr(), self.n_local, scalar_fmt, self.xchg,
+                                           h_out_pinned.data_ptr()))
+            return
         if self.d_scalars is None or self.d_scalars.numel() != h_scalars_pinned.numel():
             self.d_scalars = torch.empty(h_scalars_pinned.numel(), dtype=torch.uint8, device="cuda")
         self.d_scalars.copy_(h_scalars_pinned, non_blocking=True)

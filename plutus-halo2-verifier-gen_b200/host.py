@@ -47,9 +47,11 @@ class ParamsKZG:
     ``get_or_create_kzg_params`` returns (/root/reference/src/kzg_params.rs:33-47)."""
 
     def __init__(self, k: int, g: bytes, g_lagrange: Optional[bytes] = None, fmt: int = FMT_CANONICAL,
-                 stride: int = 96):
+                 stride: int = 96, flags: int = 0):
+        """``flags``: capi.BASES_* bits OR-ed into the format (window tables off, shard / replicate over the bound GPUs)."""
         self.k = k
         self.n = 1 << k
+        fmt |= flags
         self._g = self._register(g, fmt, stride)
         self._g_lagrange = self._register(g_lagrange, fmt, stride) if g_lagrange is not None else None
 
@@ -108,13 +110,22 @@ class KZGCommitmentScheme:
 
     @staticmethod
     def commit_batch(params: ParamsKZG, polys: Sequence[bytes], lagrange: bool = False) -> List[bytes]:
-        """All columns of one prover phase in a single launch sequence (same length each)."""
+        """All columns of one prover phase in a single call (same length each).  The columns stay where they are (one
+        buffer per polynomial, like halo2's Vecs): the library takes an array of pointers and, with several GPUs bound,
+        deals the columns out."""
         if not polys:
             return []
         h = params._g_lagrange if lagrange else params._g
         if h is None:
             raise ValueError("params were built without a Lagrange-basis table")
-        return KZGCommitmentScheme._msm(h, params.n, b"".join(polys), batch=len(polys))
+        n = len(polys[0]) // 32
+        if any(len(p) != 32 * n for p in polys):
+            raise ValueError("columns of one batch have the same length")
+        assert n <= params.n, "polynomial longer than the SRS"
+        ptrs = (C.c_void_p * len(polys))(*[addr(p) for p in polys])
+        out = C.create_string_buffer(96 * len(polys))
+        check(lib().b200zk_msm_g1_batch_ptrs(h, 0, C.addressof(ptrs), n, len(polys), FMT_CANONICAL, addr(out)))
+        return [out.raw[96 * i:96 * (i + 1)] for i in range(len(polys))]
 
 
 class EvaluationDomain:
@@ -183,10 +194,14 @@ class EvaluationDomain:
         return bytes(buf[: 32 * self.n * self.quotient_poly_degree])
 
     def lagrange_to_coeff_batch(self, polys: Sequence[bytes]) -> List[bytes]:
-        buf = bytearray(b"".join(polys))
-        self._ntt(buf, self.k, self.omega_inv, NTT_INVERSE_SCALE, batch=len(polys))
-        step = 32 * self.n
-        return [bytes(buf[i * step:(i + 1) * step]) for i in range(len(polys))]
+        """Many columns at once, each in its own buffer (pointer-array entry point; dealt out over the bound GPUs)."""
+        bufs = [bytearray(p) for p in polys]
+        if not bufs:
+            return []
+        ptrs = (C.c_void_p * len(bufs))(*[addr(b) for b in bufs])
+        om = fr_bytes(self.omega_inv)
+        check(lib().b200zk_ntt_fr_batch_ptrs(C.addressof(ptrs), len(bufs), self.k, addr(om), NTT_INVERSE_SCALE, None))
+        return [bytes(b) for b in bufs]
 
 
 class DualMSM:
@@ -230,6 +245,114 @@ class DualMSM:
 
     def eval(self) -> Tuple[bytes, bytes]:
         return self._eval(self.left), self._eval(self.right)
+
+
+class Transcript:
+    """The reference's Fiat-Shamir transcript (CardanoFriendlyBlake2b, /root/reference/src/plutus_gen/adjusted_types/mod.rs:30-72;
+    verifier twin /root/reference/aiken-verifier/aiken_halo2/lib/transcript.ak:19-106), kept inside the library so that
+    ``multi_open`` / ``multi_prepare`` advance it in the same call that does the work.  Scalars are ints, points 48-byte
+    compressed strings.  With ``proof`` given it also reads: ``read_point`` / ``read_scalar`` consume the next item and absorb it."""
+
+    def __init__(self, proof: bytes = b""):
+        h = C.c_uint64(0)
+        check(lib().b200zk_transcript_new(C.byref(h)))
+        self.handle = h.value
+        self.proof = bytes(proof)
+        self.pos = 0
+
+    def common_scalar(self, s: int) -> None:
+        b = fr_bytes(s)
+        check(lib().b200zk_transcript_common_scalar(self.handle, addr(b)))
+
+    def common_point(self, compressed: bytes) -> None:
+        assert len(compressed) == 48
+        check(lib().b200zk_transcript_common_point(self.handle, addr(compressed)))
+
+    write_scalar, write_point = common_scalar, common_point
+
+    def read_scalar(self) -> int:
+        b = self.proof[self.pos:self.pos + 32]
+        self.pos += 32
+        check(lib().b200zk_transcript_common_scalar(self.handle, addr(b)))
+        return int.from_bytes(b, "little")
+
+    def read_point(self) -> bytes:
+        b = self.proof[self.pos:self.pos + 48]
+        self.pos += 48
+        self.common_point(b)
+        return b
+
+    def squeeze_challenge(self) -> int:
+        out = C.create_string_buffer(32)
+        check(lib().b200zk_transcript_squeeze(self.handle, addr(out)))
+        return int.from_bytes(out.raw, "little")
+
+    def free(self) -> None:
+        if self.handle:
+            check(lib().b200zk_transcript_free(self.handle))
+            self.handle = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib().b200zk_transcript_free(self.handle)
+        except Exception:
+            pass
+
+
+class Guard:
+    """upstream ``DualMSM`` guard of one opening proof: accept iff e(left, [s]G2) == e(right, G2)."""
+
+    def __init__(self, handle: int, scalars: Optional[dict] = None):
+        self.handle = handle
+        self.scalars = scalars or {}
+
+    def eval(self) -> Tuple[bytes, bytes]:
+        return batch_guards([self])
+
+    def free(self) -> None:
+        if self.handle:
+            check(lib().b200zk_guard_free(self.handle))
+            self.handle = None
+
+
+def batch_guards(guards: Sequence[Guard], challenges: Optional[Sequence[int]] = None) -> Tuple[bytes, bytes]:
+    """(left, right) of sum_i c_i * guard_i: ``batch_verify`` up to the pairing
+    (/root/reference/src/circuits/schnorr_circuit.rs:224-229).  One GPU decompression batch + two ad-hoc MSMs."""
+    hs = (C.c_uint64 * len(guards))(*[g.handle for g in guards])
+    cb = b"".join(fr_bytes(c) for c in challenges) if challenges is not None else None
+    left, right = C.create_string_buffer(96), C.create_string_buffer(96)
+    check(lib().b200zk_guard_eval(C.addressof(hs), len(guards), addr(cb), addr(left), addr(right)))
+    return left.raw, right.raw
+
+
+def multi_open(params: "ParamsKZG", transcript: Transcript, polys: Sequence["FrVec"], queries: Sequence[Tuple[int, int]]) -> bytes:
+    """``KZGCommitmentScheme::multi_open`` with resident polynomials: ``queries`` = (polynomial index, point); returns the opening
+    proof f || q_evals || pi and leaves the transcript where the verifier's will be."""
+    n = polys[0].n
+    ptrs = (C.c_void_p * len(polys))(*[p.ptr for p in polys])
+    qp = (C.c_uint32 * len(queries))(*[q[0] for q in queries])
+    pts = b"".join(fr_bytes(q[1]) for q in queries)
+    out = C.create_string_buffer(48 + 32 * len(queries) + 48)
+    ln = C.c_size_t(0)
+    check(lib().b200zk_h2mo_open_dev(params._g, transcript.handle, C.addressof(ptrs), len(polys), n, C.addressof(qp), addr(pts),
+                                     len(queries), addr(out), len(out), C.byref(ln)))
+    return out.raw[:ln.value]
+
+
+def multi_prepare(transcript: Transcript, commitments: Sequence[bytes], queries: Sequence[Tuple[int, int, int]], proof: bytes) -> Guard:
+    """``KZGCommitmentScheme::multi_prepare``: ``commitments`` 48-byte compressed points, ``queries`` = (commitment index, point,
+    claimed evaluation), ``proof`` the opening proof.  Returns the guard; ``guard.scalars`` holds x1..x4, f_eval, v."""
+    cb = b"".join(commitments)
+    qc = (C.c_uint32 * len(queries))(*[q[0] for q in queries])
+    pts = b"".join(fr_bytes(q[1]) for q in queries)
+    evs = b"".join(fr_bytes(q[2]) for q in queries)
+    g = C.c_uint64(0)
+    sc = C.create_string_buffer(192)
+    check(lib().b200zk_h2mo_prepare(transcript.handle, addr(cb), len(commitments), C.addressof(qc), addr(pts), addr(evs), len(queries),
+                                    addr(proof), len(proof), C.byref(g), addr(sc)))
+    names = ("x1", "x2", "x3", "x4", "f_eval", "v")
+    return Guard(g.value, {nm: int.from_bytes(sc.raw[32 * i:32 * i + 32], "little") for i, nm in enumerate(names)})
 
 
 def g1_compress(affine: bytes) -> bytes:

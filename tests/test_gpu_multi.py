@@ -1,0 +1,45 @@
+"""The single-process multi-GPU path (b200zk_init_devices): sharded and replicated base tables, column fan-out, the fused
+peer-store exchange, concurrent host threads -- each check against the CPU oracle, in a fresh process per GPU count
+(tests/multi/run_multi.py).  Skips the counts the box does not have; on one GPU the same script still runs with a
+single bound device (the fan-out code paths degenerate, shutdown / re-init is exercised)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_gpus", [1, 2, 4, 8])
+def test_single_process_multi_gpu(n_gpus):
+    if _gpus() < n_gpus:
+        pytest.skip("needs %d GPUs" % n_gpus)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "multi", "run_multi.py"), "--gpus", str(n_gpus)],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["ok"] and len(res["checks"]) >= 30
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_process_peer_exchange(world):
+    """One process per GPU (torchrun-style): the XYZZ partials meet in rank 0's HBM through CUDA-IPC peer stores; every
+    rank ends up with the oracle's result, for device-resident and host-buffer calls."""
+    if _gpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    port = 29600 + os.getpid() % 300
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(ROOT, "tests", "multi", "run_xchg.py")], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines and all(l["ok"] for l in lines)

@@ -221,3 +221,57 @@ def test_compile_gates_register_allocation(zk, pyref):
     # a complete binary tree of depth d needs d registers; overflowing the 48-register file would take 2^48 leaves
     cg = zk.host.compile_gates([bushy(10)], 1)
     assert max(w >> 8 for w in cg.words[0::4]) <= 10
+
+
+def test_h2mo_open_restatement_is_accepted_by_the_pinned_verifier_pipeline(pyref):
+    """The checker's prover (h2mo_open) against the checker's verifier scalar pipeline (h2mo_q_eval_sets / f_eval / v, pinned to
+    Halo2MultiOpenMSM.hs:26-42 by test_oracle_kats): with the SRS secret known, commit(p) = p(s) G and the pairing check
+    e(pi, [s]G2) == e(right, G2) is s * pi == right in G1."""
+    import random
+    P = pyref
+    R = P.R_MOD
+    rnd = random.Random(21)
+    n, s = 32, rnd.randrange(R)
+    polys = [[rnd.randrange(R) for _ in range(n)] for _ in range(5)]
+    w = P.omega(5)
+    x = rnd.randrange(R)
+    queries = [(0, x), (1, x), (1, x * w % R), (2, x), (0, x * w % R), (3, x * w % R), (3, x), (3, x * P.fr_inv(w) % R), (4, x)]
+    commit = lambda c: P.g1_mul(P.G1_GEN, P.poly_eval(c, s))
+    comms = [commit(p) for p in polys]
+    evals = [P.poly_eval(polys[i], pt) for i, pt in queries]
+    t = P.Transcript()
+    for c in comms:
+        t.common_point(c)
+    proof = P.h2mo_open(polys, queries, t, commit)
+    psets, members, ev = P.h2mo_sets([(i, pt, e) for (i, pt), e in zip(queries, evals)])
+    assert len(psets) == 3 and len(proof) == 48 + 32 * 3 + 48
+    # verifier
+    t = P.Transcript(proof)
+    for c in comms:
+        t.common_point(c)
+    x1, x2 = t.squeeze(), t.squeeze()
+    f_comm = t.read_point()
+    x3 = t.squeeze()
+    pq = [t.read_scalar() for _ in psets]
+    x4 = t.squeeze()
+    pi = t.read_point()
+    cmap = [(comms[p], si, psets[si], ev[p]) for si, mem in enumerate(members) for p in mem]
+    qes = P.h2mo_q_eval_sets(cmap, len(psets), x1)
+    f_eval = P.h2mo_f_eval(psets, qes, x2, x3, pq)
+    v = P.h2mo_v(f_eval, x4, pq)
+    right = P.INF
+    for si, mem in enumerate(members):
+        xp = pow(x4, si, R)
+        for p in mem:
+            right = P.g1_add(right, P.g1_mul(comms[p], xp))
+            xp = xp * x1 % R
+    right = P.g1_add(right, P.g1_mul(f_comm, pow(x4, len(psets), R)))
+    right = P.g1_add(right, P.g1_mul(P.g1_neg(P.G1_GEN), v))
+    right = P.g1_add(right, P.g1_mul(pi, x3))
+    assert P.g1_mul(pi, s) == right
+    # and a wrong claimed evaluation is rejected
+    ev2 = {k: list(vv) for k, vv in ev.items()}
+    ev2[1][0] = (ev2[1][0] + 1) % R
+    cmap2 = [(comms[p], si, psets[si], ev2[p]) for si, mem in enumerate(members) for p in mem]
+    f2 = P.h2mo_f_eval(psets, P.h2mo_q_eval_sets(cmap2, len(psets), x1), x2, x3, pq)
+    assert f2 != f_eval
