@@ -190,6 +190,15 @@ int32_t b200zk_ntt_fr_batch_ptrs(uint8_t *const *data, uint32_t batch, uint32_t 
                                  const uint8_t coset_shift[32]);
 int32_t b200zk_ntt_fr_dev(void *d_data, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
                           const uint8_t coset_shift[32], void *stream);
+/* One long transform over all bound GPUs (2, 4, 8 or 16).  b200zk_ntt_fr does this by itself for log_n >= 23: four-step
+ * decomposition n = R * C (R = 2^log_r <= 2^11); GPU g transforms the columns [g C/G, (g+1) C/G) and stores row k1 of the
+ * intermediate matrix, twiddled, straight into the HBM of the GPU that owns it (the one exchange, peer stores from inside the
+ * kernel); then every GPU transforms its R/G rows.  From host memory both transpositions ride on the strided H2D / D2H copies.
+ * The resident form takes and leaves the blocks in HBM: d_in[g] = x[i1 * C + g C/G + u] as [R][C/G]; d_out[g] (may be d_in[g])
+ * receives X[g R/G + k1 + R k2] as [C][R/G].  Synchronous.  b200zk_ntt_sharded_layout reports log_r and log_c.            */
+int32_t b200zk_ntt_sharded_layout(uint32_t log_n, uint32_t *out_log_r, uint32_t *out_log_c);
+int32_t b200zk_ntt_fr_sharded_dev(void *const *d_in, void *const *d_out, uint32_t n_parts, uint32_t log_n, const uint8_t omega[32],
+                                  uint32_t flags, const uint8_t coset_shift[32]);
 
 /* ---- encodings --------------------------------------------------------------------------
  * ZCash compressed form of an affine canonical point: what the transcript absorbs and the proof
@@ -338,7 +347,8 @@ int32_t b200zk_selftest_field(uint32_t field, uint32_t op, const uint8_t *a, con
  * multiplications, 3 = XYZZ mixed additions, 4 = Fr multiplications, 5 = carry-chained IMAD.WIDE.U32.X rows
  * (as the Montgomery multiplier issues them), 6 = DFMA, 7 = IMAD.WIDE with carry-out only, 8 = IMAD.WIDE
  * paired 1:1 with IADD, 9 = IMAD.HI.U32 alone, 10 = 32-bit IMAD alone, 11 = the unfused IMAD + IMAD.HI.U32 pair with an
- * immediate multiplier.  *out_ops_per_s receives limb-MACs (0,1,5,7,8), multiplications (2,4), additions (3)
+ * immediate multiplier, 12 = Fr multiplications at 16 warps / SM (the NTT kernel's occupancy), 13 / 14 = the arithmetic of an NTT
+ * butterfly (add, sub, product; no memory) at 16 / 64 warps per SM.  *out_ops_per_s receives limb-MACs (0,1,5,7,8), multiplications (2,4,12), butterflies (13,14), additions (3)
  * or FMAs (6) per second over all SMs.                                                            */
 int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double *out_ops_per_s, double *out_ms);
 /* number of kernels this library has launched since init (bench.py's gpu_launches counter) */

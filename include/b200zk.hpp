@@ -32,6 +32,11 @@ using Fr = std::array<uint8_t, 32>;        // little-endian canonical
 using G1Affine = std::array<uint8_t, 96>;  // x || y little-endian canonical, identity = (0,0)
 
 inline void init(int device = -1) { check(b200zk_init(device)); }
+// One process, several GPUs (the reference prover is a single process, /root/reference/examples/simple_mul.rs:39-141): every
+// later commit / transform fans out over all of them.  Empty list: the first n_devices ordinals.
+inline void init_devices(const std::vector<int32_t>& ordinals, int32_t n_devices = 0) {
+    check(ordinals.empty() ? b200zk_init_devices(nullptr, n_devices) : b200zk_init_devices(ordinals.data(), (int32_t)ordinals.size()));
+}
 
 // Device residency of the two SRS tables (g: monomial basis, g_lagrange: Lagrange basis).
 class ParamsKZG {
@@ -82,6 +87,22 @@ struct KZGCommitmentScheme {
     static G1Affine commit_lagrange(const ParamsKZG& params, const std::vector<Fr>& poly) {
         if (!params.g_lagrange()) throw Error(B200ZK_ERR_INVALID_ARG, "params built without a Lagrange-basis table");
         return msm(params.g_lagrange(), params.n(), poly);
+    }
+    // all columns of one prover phase in a single call; every polynomial stays in its own vector (pointer-array entry point),
+    // with several GPUs bound the columns are dealt out or, for a partitioned table, every column is sharded by point range
+    static std::vector<G1Affine> commit_batch(const ParamsKZG& params, const std::vector<const std::vector<Fr>*>& polys, bool lagrange = false) {
+        std::vector<G1Affine> out(polys.size());
+        if (polys.empty()) return out;
+        const uint64_t h = lagrange ? params.g_lagrange() : params.g();
+        if (!h) throw Error(B200ZK_ERR_INVALID_ARG, "params built without a Lagrange-basis table");
+        std::vector<const uint8_t*> ptrs;
+        for (auto* p : polys) {
+            if (p->size() != polys[0]->size() || p->size() > params.n()) throw Error(B200ZK_ERR_INVALID_ARG, "columns of one batch have the same length, at most the SRS size");
+            ptrs.push_back(reinterpret_cast<const uint8_t*>(p->data()));
+        }
+        check(b200zk_msm_g1_batch_ptrs(h, 0, ptrs.data(), polys[0]->size(), (uint32_t)polys.size(), B200ZK_FMT_CANONICAL,
+                                       reinterpret_cast<uint8_t*>(out.data())));
+        return out;
     }
 
 private:
@@ -248,6 +269,89 @@ private:
     uint64_t h_ = 0;
     uint32_t ek_, ncol_;
 };
+
+// ---------------------------------------------------------------------------------------------------
+// The composed flows (csrc/h2mo.cu): transcript, multi_open with resident polynomials, multi_prepare, guards.
+// ---------------------------------------------------------------------------------------------------
+using G1Compressed = std::array<uint8_t, 48>;
+
+// CardanoFriendlyBlake2b (/root/reference/src/plutus_gen/adjusted_types/mod.rs:30-72)
+class Transcript {
+public:
+    Transcript() { check(b200zk_transcript_new(&h_)); }
+    ~Transcript() { if (h_) b200zk_transcript_free(h_); }
+    Transcript(const Transcript&) = delete;
+    Transcript& operator=(const Transcript&) = delete;
+    void common_scalar(const Fr& s) { check(b200zk_transcript_common_scalar(h_, s.data())); }
+    void common_point(const G1Compressed& p) { check(b200zk_transcript_common_point(h_, p.data())); }
+    Fr squeeze_challenge() { Fr c{}; check(b200zk_transcript_squeeze(h_, c.data())); return c; }
+    uint64_t handle() const { return h_; }
+
+private:
+    uint64_t h_ = 0;
+};
+
+struct ProverQuery { uint32_t poly; Fr point; };                 // open polynomial `poly` at `point`
+struct VerifierQuery { uint32_t commitment; Fr point; Fr eval; }; // commitment is claimed to evaluate to `eval` at `point`
+
+// KZGCommitmentScheme::multi_open (message order /root/reference/src/plutus_gen/extraction/pcs/kzg.rs:55-79): returns
+// f || q_evals || pi and leaves the transcript where the verifier's will be
+inline std::vector<uint8_t> multi_open(const ParamsKZG& params, Transcript& t, const std::vector<const DeviceFr*>& polys,
+                                       const std::vector<ProverQuery>& queries) {
+    std::vector<const void*> ptrs;
+    for (auto* p : polys) ptrs.push_back(p->ptr());
+    std::vector<uint32_t> qp;
+    std::vector<uint8_t> pts;
+    for (auto& q : queries) { qp.push_back(q.poly); pts.insert(pts.end(), q.point.begin(), q.point.end()); }
+    std::vector<uint8_t> proof(48 + 32 * queries.size() + 48);
+    size_t len = 0;
+    check(b200zk_h2mo_open_dev(params.g(), t.handle(), ptrs.data(), (uint32_t)polys.size(), polys.empty() ? 0 : polys[0]->size(), qp.data(),
+                               pts.data(), (uint32_t)queries.size(), proof.data(), proof.size(), &len));
+    proof.resize(len);
+    return proof;
+}
+
+// The verifier's guard (upstream DualMSM): accept iff e(left, [s]G2) == e(right, G2); the pairing stays with the caller.
+class Guard {
+public:
+    explicit Guard(uint64_t h) : h_(h) {}
+    ~Guard() { if (h_) b200zk_guard_free(h_); }
+    Guard(Guard&& o) noexcept : h_(o.h_) { o.h_ = 0; }
+    Guard(const Guard&) = delete;
+    Guard& operator=(const Guard&) = delete;
+    std::pair<G1Affine, G1Affine> eval() const {
+        G1Affine l{}, r{};
+        check(b200zk_guard_eval(&h_, 1, nullptr, l.data(), r.data()));
+        return {l, r};
+    }
+    uint64_t handle() const { return h_; }
+
+private:
+    uint64_t h_;
+};
+// KZGCommitmentScheme::multi_prepare (/root/reference/aiken-verifier/aiken_halo2/lib/halo2_kzg.ak:15-171)
+inline Guard multi_prepare(Transcript& t, const std::vector<G1Compressed>& commitments, const std::vector<VerifierQuery>& queries,
+                           const std::vector<uint8_t>& proof) {
+    std::vector<uint32_t> qc;
+    std::vector<uint8_t> pts, evs;
+    for (auto& q : queries) {
+        qc.push_back(q.commitment);
+        pts.insert(pts.end(), q.point.begin(), q.point.end());
+        evs.insert(evs.end(), q.eval.begin(), q.eval.end());
+    }
+    uint64_t g = 0;
+    check(b200zk_h2mo_prepare(t.handle(), reinterpret_cast<const uint8_t*>(commitments.data()), (uint32_t)commitments.size(), qc.data(),
+                              pts.data(), evs.data(), (uint32_t)queries.size(), proof.data(), proof.size(), &g, nullptr));
+    return Guard(g);
+}
+// batch_verify up to the pairing (/root/reference/src/circuits/schnorr_circuit.rs:224-229): sum_i challenges[i] * guards[i]
+inline std::pair<G1Affine, G1Affine> batch_guards(const std::vector<const Guard*>& guards, const std::vector<Fr>& challenges) {
+    std::vector<uint64_t> hs;
+    for (auto* g : guards) hs.push_back(g->handle());
+    G1Affine l{}, r{};
+    check(b200zk_guard_eval(hs.data(), (uint32_t)hs.size(), reinterpret_cast<const uint8_t*>(challenges.data()), l.data(), r.data()));
+    return {l, r};
+}
 
 // Decompresses the commitments a proof carries (48 bytes each); throws on a bad encoding like the in-tree
 // uncompress (/root/reference/plinth-verifier/plutus-halo2/src/Plutus/Crypto/Halo2/CompressUncompress.hs:70-100).

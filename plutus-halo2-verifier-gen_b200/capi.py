@@ -78,6 +78,8 @@ SIGNATURES = {
     "b200zk_ntt_fr_batch": (C.c_int32, [_u8p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, _u8p]),
     "b200zk_ntt_fr_batch_ptrs": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, _u8p]),
     "b200zk_ntt_fr_dev": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, _u8p, C.c_void_p]),
+    "b200zk_ntt_sharded_layout": (C.c_int32, [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "b200zk_ntt_fr_sharded_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint32, _u8p]),
     "b200zk_g1_compress": (C.c_int32, [_u8p, _u8p]),
     "b200zk_dev_alloc": (C.c_int32, [C.POINTER(C.c_void_p), C.c_size_t]),
     "b200zk_dev_free": (C.c_int32, [C.c_void_p]),

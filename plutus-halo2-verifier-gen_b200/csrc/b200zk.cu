@@ -148,6 +148,35 @@ struct CosetKey {
     }
 };
 
+// tables of one GPU's share of a multi-GPU transform (n = R * C, GPU g owns columns [g C/G, (g+1) C/G) in the first step)
+struct ShardPlan {
+    uint32_t log_r = 0, log_c = 0;
+    uint32_t* tw_local = nullptr;   // omega_R^e, e < R/2
+    uint32_t* tw1 = nullptr;        // [u][k]: (1/n) * omega^((g C/G + u) k)
+};
+struct ShardKey {
+    uint32_t log_n, inverse, parts, part;
+    uint8_t omega[32];
+    bool operator<(const ShardKey& o) const {
+        if (log_n != o.log_n) return log_n < o.log_n;
+        if (inverse != o.inverse) return inverse < o.inverse;
+        if (parts != o.parts) return parts < o.parts;
+        if (part != o.part) return part < o.part;
+        return memcmp(omega, o.omega, 32) < 0;
+    }
+};
+struct ShardCosetKey {
+    uint32_t log_n, parts, part, out;
+    uint8_t shift[32];
+    bool operator<(const ShardCosetKey& o) const {
+        if (log_n != o.log_n) return log_n < o.log_n;
+        if (parts != o.parts) return parts < o.parts;
+        if (part != o.part) return part < o.part;
+        if (out != o.out) return out < o.out;
+        return memcmp(shift, o.shift, 32) < 0;
+    }
+};
+
 // one in-flight MSM or NTT: stream, scratch, staging
 constexpr int NSLOT = 2;
 struct Slot {
@@ -161,7 +190,13 @@ struct Slot {
         len_off, order, heavy, heavy_items, adhoc, buckets2, aff_a, aff_b, aff_pre, redS[2], redA[2], scan_tmp[2], out_mont, out_canon,
         stage, flag;
     // NTT workspace
-    DevBuf ntt_data, ntt_tmp[2];
+    DevBuf ntt_data, ntt_tmp[2], ntt_b;
+    cudaEvent_t xdev_ev = nullptr;       // "my column pass has stored everything into its peers" (multi-GPU transform)
+    // batch pipeline: the short, latency-bound phases of an MSM (sort, tail) run on a high-priority stream, the long
+    // integer-bound accumulation on a low-priority one, so that the sort / tail of one half of a batch are dispatched into
+    // the accumulation of the other half instead of waiting behind it
+    cudaStream_t hi = nullptr, lo = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_sorted = nullptr, ev_acc = nullptr, ev_done = nullptr;
     PinBuf h_out;
     // a "_dev" caller's stream is ordered against the previous user of the slot's scratch
     cudaEvent_t ws_event = nullptr;
@@ -175,7 +210,7 @@ struct Slot {
         return {&scalars, &counts, &offsets, &cursor, &ntask, &task_off, &entries, &task_bucket, &task_start, &task_len, &buckets,
                 &partials, &len_hist, &len_off, &order, &heavy, &heavy_items, &adhoc, &buckets2, &aff_a, &aff_b, &aff_pre, &redS[0],
                 &redS[1], &redA[0], &redA[1], &scan_tmp[0], &scan_tmp[1], &out_mont, &out_canon, &stage, &flag, &ntt_data, &ntt_tmp[0],
-                &ntt_tmp[1]};
+                &ntt_tmp[1], &ntt_b};
     }
 };
 
@@ -229,10 +264,11 @@ struct Dev {
     std::mutex gen_mu;                // d_gen only
     std::condition_variable cv;       // a slot became free
     Slot slots[NSLOT];
-    unsigned rr = 0;
     cudaStream_t stream = nullptr;    // registration, table read-back, ext-TU host entry points
     std::map<NttKey, NttPlan> ntt_plans;
     std::map<CosetKey, uint32_t*> coset_tables;
+    std::map<ShardKey, ShardPlan> shard_plans;        // multi-GPU transforms: this GPU's tables
+    std::map<ShardCosetKey, uint32_t*> shard_cosets;
     uint32_t* fixed_table = nullptr;  // 8 x 256 multiples of G for the synthetic-base generator
     uint32_t* d_gen = nullptr;        // generator of G1, Montgomery affine
     bool ntt_attr_set = false;
@@ -260,7 +296,8 @@ uint32_t g_tune_c = 0, g_tune_smax = 0, g_tune_variant = 6, g_tune_no_tables = 0
 bool g_profiling = false;
 Ctx* g_prof_ctx = nullptr;
 Slot* g_prof_slot = nullptr;
-int g_ntt_variant = 1;            // 1: two CTAs per SM (default); 0: one CTA per SM.  B200ZK_NTT_VARIANT overrides.
+int g_ntt_variant = 7;            // 7: two CTAs per SM, compile-time twiddle exponents in the lowest sweep (default); 1: without them;
+                                  // 0: one CTA per SM; 2..6 experiments.  B200ZK_NTT_VARIANT overrides.
 int64_t g_chunk_min = 1ll << 23;  // a single host-buffer MSM of at least this many points streams its scalars in two pieces
 size_t g_batch_stream_min = (size_t)128 << 20;
 int64_t g_ntt_pipe_min = 32ll << 20;
@@ -307,11 +344,12 @@ int32_t ctx_for_pointer(const void* p, Ctx** out) {
 Slot* acquire_slot(Ctx& c) {
     std::unique_lock<std::mutex> lk(c.mu);
     for (;;) {
+        // lowest free slot: a sequential caller keeps reusing slot 0 (warm workspaces, half the memory); the second slot
+        // only comes into play when two calls overlap
         for (int k = 0; k < NSLOT; k++) {
-            Slot& s = c.slots[(c.rr + k) % NSLOT];
+            Slot& s = c.slots[k];
             if (!s.busy) {
                 s.busy = true;
-                c.rr = (unsigned)(s.id + 1);
                 return &s;
             }
         }
@@ -361,6 +399,21 @@ int32_t ws_leave(Slot& sl, cudaStream_t s) {
     sl.ws_stream = s;
     sl.ws_used = true;
     return B200ZK_OK;
+}
+int32_t slot_pipe_streams(Slot& sl) {
+    if (sl.hi) return B200ZK_OK;
+    int least = 0, greatest = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CU(cudaStreamCreateWithPriority(&sl.hi, cudaStreamNonBlocking, greatest));
+    CU(cudaStreamCreateWithPriority(&sl.lo, cudaStreamNonBlocking, least));
+    for (cudaEvent_t* e : {&sl.ev_fork, &sl.ev_sorted, &sl.ev_acc, &sl.ev_done}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return B200ZK_OK;
+}
+Slot* try_acquire_slot(Ctx& c) {
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (int k = 0; k < NSLOT; k++)
+        if (!c.slots[k].busy) { c.slots[k].busy = true; return &c.slots[k]; }
+    return nullptr;
 }
 int32_t slot_streams(Slot& sl) {
     if (!sl.copy_stream) {
@@ -548,7 +601,7 @@ struct MsmChunk {
 };
 int32_t msm_run(Ctx& c, Slot& sl, const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, uint32_t batch,
                 uint32_t scalar_fmt, uint32_t* d_out_mont, uint32_t* d_out_canon, cudaStream_t s, uint32_t* d_out_xyzz = nullptr,
-                const MsmChunk* ck = nullptr, const XchgArgs* xa = nullptr) {
+                const MsmChunk* ck = nullptr, const XchgArgs* xa = nullptr, cudaStream_t s_acc = nullptr) {
     XchgArgs xnone{};
     if (batch == 0) return B200ZK_OK;
     if (n == 0) {
@@ -653,6 +706,12 @@ int32_t msm_run(Ctx& c, Slot& sl, const BaseTable* tab, const uint32_t* d_bases,
     LAUNCH(msm_heavy_list_kernel, bgrid, 256, 0, s, (const uint32_t*)ntask, NBt, hv);
     CU(cudaMemsetAsync(buckets, 0, NBt * 192, s));
     TRY(prof_mark(sl, 1, s));
+    const cudaStream_t s_main = s;
+    if (s_acc) {   // the accumulation runs on its own (low-priority) stream between two events
+        CU(cudaEventRecord(sl.ev_sorted, s_main));
+        CU(cudaStreamWaitEvent(s_acc, sl.ev_sorted, 0));
+        s = s_acc;
+    }
     {
         unsigned agrid = (unsigned)((max_tasks + 127) / 128);
         const uint32_t *tb = sl.task_bucket.as<uint32_t>(), *ts = sl.task_start.as<uint32_t>(), *tl = sl.task_len.as<uint32_t>();
@@ -679,6 +738,11 @@ int32_t msm_run(Ctx& c, Slot& sl, const BaseTable* tab, const uint32_t* d_bases,
             }
             default: LAUNCH(msm_accumulate_kernel, agrid, 128, 0, s, d_bases, (const uint32_t*)entries, tb, ts, tl, (const uint32_t*)order, ntp, buckets, partials); break;
         }
+    }
+    if (s_acc) {
+        CU(cudaEventRecord(sl.ev_acc, s_acc));
+        s = s_main;
+        CU(cudaStreamWaitEvent(s, sl.ev_acc, 0));
     }
     TRY(prof_mark(sl, 2, s));
     LAUNCH(msm_collapse_kernel, (unsigned)(c.prop.multiProcessorCount * 4), 128, 0, s, (const uint32_t*)ntask,
@@ -729,6 +793,42 @@ int32_t msm_run(Ctx& c, Slot& sl, const BaseTable* tab, const uint32_t* d_bases,
     TRY(prof_mark(sl, 3, s));
     TRY(ws_leave(sl, s));
     sl.last_plan = pl;
+    return B200ZK_OK;
+}
+
+// A batch of columns on caller stream s.  With a second free slot and enough work the batch is cut in two halves that run as
+// two pipelines (sort, tail on each slot's high-priority stream; accumulate on its low-priority stream): the second half's
+// sort is dispatched into the first half's accumulation and the first half's tail into the second half's accumulation.
+// Measured (B200, 18 columns of 2^17 prover-like scalars / 18 of 2^19): see profiles/README.md.
+int32_t msm_run_batch(Ctx& c, Slot& sl, const BaseTable* tab, const uint32_t* d_bases, const uint32_t* d_scalars, uint64_t n, uint32_t batch,
+                      uint32_t scalar_fmt, uint32_t* d_out_mont, uint32_t* d_out_canon, cudaStream_t s, const XchgArgs* xa) {
+    static int64_t pipe_min = -1;
+    // off by default: measured on B200 (profiles/r02_batch_pipeline.jsonl) the two pipelines do not beat one launch sequence over
+    // the whole batch (18 x 2^17: 7.60 ms in one sequence, 8.96 ms piped; 18 x 2^19: 28.7 / 29.1 ms)
+    if (pipe_min < 0) { const char* v = getenv("B200ZK_BATCH_PIPE_MIN_POINTS"); pipe_min = v ? atoll(v) : 0; }
+    Slot* sl2 = nullptr;
+    if (batch >= 2 && pipe_min > 0 && (int64_t)(n * batch) >= pipe_min) sl2 = try_acquire_slot(c);
+    if (!sl2) return msm_run(c, sl, tab, d_bases, d_scalars, n, batch, scalar_fmt, d_out_mont, d_out_canon, s, nullptr, nullptr, xa);
+    struct Release { Ctx& c; Slot* s; ~Release() { release_slot(c, s); } } rel{c, sl2};
+    Slot* half_slot[2] = {&sl, sl2};
+    TRY(slot_pipe_streams(sl));
+    TRY(slot_pipe_streams(*sl2));
+    const uint32_t bA = (batch + 1) / 2;
+    CU(cudaEventRecord(sl.ev_fork, s));
+    for (int h = 0; h < 2; h++) {
+        Slot& hs = *half_slot[h];
+        const uint32_t b0 = h ? bA : 0, cnt = h ? batch - bA : bA;
+        CU(cudaStreamWaitEvent(hs.hi, sl.ev_fork, 0));
+        XchgArgs xh{};
+        if (xa) { xh = *xa; xh.col0 = xa->col0 + b0; }
+        TRY(msm_run(c, hs, tab, d_bases, d_scalars + 8 * (size_t)n * b0, n, cnt, scalar_fmt, d_out_mont ? d_out_mont + 24 * (size_t)b0 : nullptr,
+                    d_out_canon ? d_out_canon + 24 * (size_t)b0 : nullptr, hs.hi, nullptr, nullptr, xa ? &xh : nullptr, hs.lo));
+        CU(cudaEventRecord(hs.ev_done, hs.hi));
+    }
+    for (int h = 0; h < 2; h++) CU(cudaStreamWaitEvent(s, half_slot[h]->ev_done, 0));
+    // later users of either slot's scratch order themselves behind s
+    TRY(ws_leave(sl, s));
+    TRY(ws_leave(*sl2, s));
     return B200ZK_OK;
 }
 
@@ -849,6 +949,8 @@ int32_t ntt_set_attrs(Ctx& c) {
     CU(cudaFuncSetAttribute(ntt_pass_kernel_call3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
     CU(cudaFuncSetAttribute(ntt_pass_kernel_plain2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
     CU(cudaFuncSetAttribute(ntt_pass_kernel_wl2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+    CU(cudaFuncSetAttribute(ntt_pass_kernel_tw2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM_TW));
+    CU(cudaFuncSetAttribute(ntt_pass_kernel_lb0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
     c.ntt_attr_set = true;
     return B200ZK_OK;
 }
@@ -862,8 +964,13 @@ int32_t ntt_check_args(uint32_t log_n, uint32_t flags, const uint8_t* coset_shif
     return B200ZK_OK;
 }
 
+struct NttExtra {
+    uint32_t* out_final = nullptr;       // the last pass writes here instead of d_data
+    uint32_t t_out = 0;                  // 1 + log2(batch): ... transposed, element (poly, i) at (i << log2 batch) + poly
+    const uint32_t* out_scale = nullptr; // multiplier table indexed like the (transposed) output
+};
 int32_t ntt_run(Ctx& c, Slot& sl, uint32_t* d_data, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags,
-                const uint8_t* coset_shift, cudaStream_t s) {
+                const uint8_t* coset_shift, cudaStream_t s, const NttExtra* ex = nullptr) {
     TRY(ntt_check_args(log_n, flags, coset_shift));
     if (batch == 0) return B200ZK_OK;
     bool inverse = (flags & B200ZK_NTT_INVERSE_SCALE) != 0;
@@ -890,7 +997,7 @@ int32_t ntt_run(Ctx& c, Slot& sl, uint32_t* d_data, uint32_t batch, uint32_t log
     TRY(prof_mark(sl, 0, s));
     for (uint32_t i = 0; i < pl->npass; i++) {
         bool last = (i + 1 == pl->npass);
-        uint32_t* dst = last ? d_data : bufs[i & 1];
+        uint32_t* dst = last ? ((ex && ex->out_final) ? ex->out_final : d_data) : bufs[i & 1];
         if (pl->npass == 3 && i == 1) dst = bufs[1];
         NttPassArgs a;
         memset(&a, 0, sizeof a);
@@ -900,6 +1007,10 @@ int32_t ntt_run(Ctx& c, Slot& sl, uint32_t* d_data, uint32_t batch, uint32_t log
         a.tw_pass = pl->tw_pass[i];
         a.in_scale = (i == 0 && (flags & B200ZK_NTT_COSET_IN)) ? coset : nullptr;
         a.out_scale = (last && (flags & B200ZK_NTT_COSET_OUT)) ? coset : nullptr;
+        if (last && ex) {
+            if (ex->out_scale) a.out_scale = ex->out_scale;
+            a.t_out = ex->t_out;
+        }
         a.scalar = (last && inverse && pl->npass == 1) ? pl->ninv : nullptr;
         a.reduce_in = (i == 0 && !(flags & B200ZK_NTT_MONT)) ? 1 : 0;
         a.log_n = log_n;
@@ -913,7 +1024,9 @@ int32_t ntt_run(Ctx& c, Slot& sl, uint32_t* d_data, uint32_t batch, uint32_t log
         else if (ntt_variant == 3) LAUNCH(ntt_pass_kernel_call3, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         else if (ntt_variant == 4) LAUNCH(ntt_pass_kernel_plain2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         else if (ntt_variant == 5) LAUNCH(ntt_pass_kernel_wl2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
-        else LAUNCH(ntt_pass_kernel_occ2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+        else if (ntt_variant == 6) LAUNCH(ntt_pass_kernel_tw2, (unsigned)ctas, NTT_THREADS, NTT_SMEM_TW, s, a);
+        else if (ntt_variant == 1) LAUNCH(ntt_pass_kernel_occ2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+        else LAUNCH(ntt_pass_kernel_lb0, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         TRY(prof_mark(sl, (int)i + 1, s));
         src = dst;
         log_s += pl->deg[i];
@@ -1049,11 +1162,12 @@ int32_t msm_host_device(Ctx& c, Slot& sl, const BaseTable* tab, uint64_t bases_o
             TRY(upload_columns(src, col0 + bA, bB, i0, n, reinterpret_cast<uint8_t*>(d_sc32 + 8 * (size_t)n * bA), sl.copy_stream));
             CU(cudaEventRecord(sl.copy_ev[1], sl.copy_stream));
             CU(cudaStreamWaitEvent(s, sl.copy_ev[1], 0));
-            TRY(msm_run(c, sl, tab, d_bases, d_sc32 + 8 * (size_t)n * bA, n, bB, scalar_fmt, nullptr, d_out ? d_out + 24 * (size_t)bA : nullptr,
-                        s, nullptr, nullptr, area ? &xb : nullptr));
+            TRY(msm_run_batch(c, sl, tab, d_bases, d_sc32 + 8 * (size_t)n * bA, n, bB, scalar_fmt, nullptr, d_out ? d_out + 24 * (size_t)bA : nullptr,
+                              s, area ? &xb : nullptr));
         } else {
             TRY(upload_columns(src, col0, gcols, i0, n, reinterpret_cast<uint8_t*>(d_sc32), s));
-            TRY(msm_run(c, sl, tab, d_bases, d_sc32, n, gcols, scalar_fmt, nullptr, d_out, s, nullptr, nullptr, xp));
+            if (gcols >= 2) TRY(msm_run_batch(c, sl, tab, d_bases, d_sc32, n, gcols, scalar_fmt, nullptr, d_out, s, xp));
+            else TRY(msm_run(c, sl, tab, d_bases, d_sc32, n, gcols, scalar_fmt, nullptr, d_out, s, nullptr, nullptr, xp));
         }
     }
     const bool readback = !area || area->fetch;
@@ -1231,6 +1345,211 @@ int32_t ntt_host_device(Ctx& c, Slot& sl, const PolySrc& src, uint32_t p0, uint3
     return B200ZK_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// one large transform over all bound GPUs (worth it at 2^23..2^24 because the transform is bound by the integer
+// pipe): four-step decomposition n = R * C,
+//   X[k1 + R k2] = sum_{i2} (w^R)^(i2 k2) * w^(i2 k1) * sum_{i1} (w^C)^(i1 k1) x[i1 C + i2].
+// GPU g takes the columns i2 in [g C/G, (g+1) C/G) -- from host memory that is a strided copy, the DMA does the first
+// transposition -- runs the R-point column transforms in ONE pass (R <= 2^11) whose store multiplies by w^(i2 k1) and writes
+// row k1 straight into the HBM of the GPU that owns it (the single exchange, fused into the kernel as peer stores); after a
+// cross-GPU event every GPU runs its R/G row transforms of length C, the last pass storing transposed so that natural
+// order is again one strided copy away.  Layouts of the resident form: in [R][C/G] per GPU, out [C][R/G] per GPU.
+// ------------------------------------------------------------------------------------------
+struct HostBarrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    int n, waiting = 0, gen = 0;
+    bool failed = false;
+    explicit HostBarrier(int parties) : n(parties) {}
+    // returns false if any party reported a failure (everybody then leaves)
+    bool arrive(bool ok) {
+        std::unique_lock<std::mutex> lk(mu);
+        if (!ok) failed = true;
+        int g = gen;
+        if (++waiting == n) { waiting = 0; gen++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+        return !failed;
+    }
+};
+
+void ntt_shard_shape(uint32_t log_n, int parts, uint32_t* log_r, uint32_t* log_c) {
+    uint32_t lg = 0;
+    while ((1 << lg) < parts) lg++;
+    uint32_t r = std::min<uint32_t>(NTT_LOGB, log_n - lg);   // C >= parts
+    *log_r = r;
+    *log_c = log_n - r;
+}
+
+int32_t ntt_get_shard_plan(Ctx& c, uint32_t log_n, const uint8_t omega[32], bool inverse, int parts, int part, ShardPlan** out) {
+    std::lock_guard<std::mutex> lk(c.mu);
+    ShardKey key;
+    key.log_n = log_n; key.inverse = inverse ? 1 : 0; key.parts = (uint32_t)parts; key.part = (uint32_t)part;
+    memcpy(key.omega, omega, 32);
+    auto it = c.shard_plans.find(key);
+    if (it != c.shard_plans.end()) { *out = &it->second; return B200ZK_OK; }
+    cudaStream_t s = c.stream;
+    ShardPlan pl;
+    ntt_shard_shape(log_n, parts, &pl.log_r, &pl.log_c);
+    const uint64_t R = 1ull << pl.log_r, C = 1ull << pl.log_c, Cl = C / parts;
+    uint32_t *d_omega = nullptr, *d_ninv = nullptr;
+    CU(cudaMalloc(&d_omega, 64));
+    d_ninv = d_omega + 8;
+    TRY(upload_fr_mont(omega, d_omega, s));
+    if (inverse) LAUNCH(fr_inv_pow2_kernel, 1, 1, 0, s, d_ninv, log_n);
+    uint64_t cnt = pl.log_r ? (R >> 1) : 1;
+    CU(cudaMalloc(&pl.tw_local, cnt * 32));
+    LAUNCH(fr_powers_kernel, (unsigned)((cnt + 127) / 128), 128, 0, s, pl.tw_local, (const uint32_t*)d_omega, (const uint32_t*)nullptr, cnt, C, 0u, 0u);
+    CU(cudaMalloc(&pl.tw1, Cl * R * 32));
+    LAUNCH(fr_power_block_kernel, (unsigned)((Cl * R + 127) / 128), 128, 0, s, pl.tw1, (const uint32_t*)d_omega,
+           inverse ? (const uint32_t*)d_ninv : (const uint32_t*)nullptr, Cl * R, pl.log_r, (uint64_t)part * Cl);
+    CU(cudaStreamSynchronize(s));
+    CU(cudaFree(d_omega));
+    auto ins = c.shard_plans.emplace(key, pl);
+    *out = &ins.first->second;
+    return B200ZK_OK;
+}
+
+int32_t ntt_get_shard_coset(Ctx& c, uint32_t log_n, const uint8_t shift[32], int parts, int part, bool out_side, uint32_t** out) {
+    std::lock_guard<std::mutex> lk(c.mu);
+    ShardCosetKey key;
+    key.log_n = log_n; key.parts = (uint32_t)parts; key.part = (uint32_t)part; key.out = out_side ? 1 : 0;
+    memcpy(key.shift, shift, 32);
+    auto it = c.shard_cosets.find(key);
+    if (it != c.shard_cosets.end()) { *out = it->second; return B200ZK_OK; }
+    cudaStream_t s = c.stream;
+    uint32_t log_r, log_c;
+    ntt_shard_shape(log_n, parts, &log_r, &log_c);
+    const uint64_t R = 1ull << log_r, C = 1ull << log_c, Cl = C / parts, Rl = R / parts;
+    uint32_t *d_shift = nullptr, *tab = nullptr;
+    CU(cudaMalloc(&d_shift, 32));
+    TRY(upload_fr_mont(shift, d_shift, s));
+    CU(cudaMalloc(&tab, (R * C / parts) * 32));
+    if (!out_side)   // like the input slice [i1][u]: shift^(i1 C + part Cl + u)
+        LAUNCH(fr_power_grid_kernel, (unsigned)((R * Cl + 127) / 128), 128, 0, s, tab, (const uint32_t*)d_shift, R, Cl, C, (uint64_t)1, (uint64_t)part * Cl);
+    else             // like the output slice [k2][k1l]: shift^(k2 R + part Rl + k1l)
+        LAUNCH(fr_power_grid_kernel, (unsigned)((C * Rl + 127) / 128), 128, 0, s, tab, (const uint32_t*)d_shift, C, Rl, R, (uint64_t)1, (uint64_t)part * Rl);
+    CU(cudaStreamSynchronize(s));
+    CU(cudaFree(d_shift));
+    c.shard_cosets[key] = tab;
+    *out = tab;
+    return B200ZK_OK;
+}
+
+// omega^(2^k) as canonical bytes, on the host with the kernels' field code
+void fr_pow2k_host(const uint8_t in[32], uint32_t k, uint8_t out[32]) {
+    Fr v;
+    memcpy(v.l, in, 32);
+    fe_reduce_loose(v);
+    v = fe_to_mont(v);
+    for (uint32_t i = 0; i < k; i++) v = fe_sqr(v);
+    v = fe_from_mont(v);
+    memcpy(out, v.l, 32);
+}
+
+struct ShardIO {
+    uint8_t* host = nullptr;                 // natural-order host buffer (in place), or
+    void* const* d_in = nullptr;             // per GPU: [R][C/G] column block ...
+    void* const* d_out = nullptr;            // ... and [C][R/G] result block (may alias d_in)
+};
+
+int32_t ntt_sharded(const ShardIO& io, uint32_t log_n, const uint8_t omega[32], uint32_t flags, const uint8_t* coset_shift) {
+    TRY(ntt_check_args(log_n, flags, coset_shift));
+    const int D = (int)g_devs.size();
+    if (D < 2 || (D & (D - 1))) return fail(B200ZK_ERR_INVALID_ARG, "ntt: a sharded transform needs 2, 4, 8 or 16 bound GPUs");
+    uint32_t log_r, log_c;
+    ntt_shard_shape(log_n, D, &log_r, &log_c);
+    const uint64_t R = 1ull << log_r, C = 1ull << log_c;
+    if (R < (uint64_t)D || C < (uint64_t)D) return fail(B200ZK_ERR_INVALID_ARG, "ntt: transform too small to shard over the bound GPUs");
+    const uint64_t Cl = C / D, Rl = R / D;
+    const bool inverse = (flags & B200ZK_NTT_INVERSE_SCALE) != 0;
+    uint8_t omega2[32];
+    fr_pow2k_host(omega, log_r, omega2);     // w^R generates the row transforms
+    std::vector<SlotLease> leases;
+    for (auto& c : g_devs) leases.emplace_back(*c);
+    std::vector<uint32_t*> peerB(D, nullptr);
+    HostBarrier bar(D);
+    std::vector<Job> jobs;
+    for (int g = 0; g < D; g++) {
+        Ctx* c = g_devs[g].get();
+        Slot* sl = leases[g].s;
+        jobs.push_back({c, [=, &peerB, &bar, &leases, &io]() -> int32_t {
+            cudaStream_t s = sl->stream;
+            const size_t slice = (size_t)(R * Cl) * 32;          // = n / D elements
+            ShardPlan* pl = nullptr;
+            uint32_t *cos_in = nullptr, *cos_out = nullptr;
+            // ---- phase 0: buffers and tables; publish where the peers must store
+            auto phase0 = [&]() -> int32_t {
+                TRY(sl->ntt_b.ensure(slice));
+                if (io.host) TRY(sl->ntt_data.ensure(slice));
+                TRY(ntt_get_shard_plan(*c, log_n, omega, inverse, D, g, &pl));
+                if (flags & B200ZK_NTT_COSET_IN) TRY(ntt_get_shard_coset(*c, log_n, coset_shift, D, g, false, &cos_in));
+                if (flags & B200ZK_NTT_COSET_OUT) TRY(ntt_get_shard_coset(*c, log_n, coset_shift, D, g, true, &cos_out));
+                if (!sl->xdev_ev) CU(cudaEventCreateWithFlags(&sl->xdev_ev, cudaEventDisableTiming));
+                TRY(ntt_set_attrs(*c));
+                peerB[g] = sl->ntt_b.as<uint32_t>();
+                return B200ZK_OK;
+            };
+            int32_t rc = phase0();
+            if (!bar.arrive(rc == B200ZK_OK)) return rc != B200ZK_OK ? rc : fail(B200ZK_ERR_CUDA, "ntt: another GPU failed to set up");
+            // ---- phase 1: my columns up (strided), column pass with the exchange fused into its store
+            uint32_t* A = io.host ? sl->ntt_data.as<uint32_t>() : reinterpret_cast<uint32_t*>(io.d_in[g]);
+            uint32_t* OUT = io.host ? A : reinterpret_cast<uint32_t*>(io.d_out[g]);
+            auto phase1 = [&]() -> int32_t {
+                TRY(ws_enter(*sl, s));
+                if (io.host)
+                    CU(cudaMemcpy2DAsync(A, Cl * 32, io.host + (size_t)g * Cl * 32, C * 32, Cl * 32, R, cudaMemcpyHostToDevice, s));
+                NttPassArgs a;
+                memset(&a, 0, sizeof a);
+                a.in = A;
+                a.tw_local = pl->tw_local;
+                a.tw_pass = pl->tw1;
+                a.in_scale = cos_in;
+                a.reduce_in = (flags & B200ZK_NTT_MONT) ? 0 : 1;
+                a.log_n = log_r + (uint32_t)(log_c - (uint32_t)__builtin_ctz((unsigned)D));
+                a.deg = log_r;
+                a.log_s = 0;
+                a.log_cols = a.log_n - log_r;
+                a.total_cols = Cl;
+                a.scatter = 1;
+                a.log_rl = log_r - (uint32_t)__builtin_ctz((unsigned)D);
+                a.log_c = log_c;
+                a.col0 = (uint32_t)(g * Cl);
+                for (int h = 0; h < D; h++) a.peer[h] = peerB[h];
+                uint64_t ctas = (R * Cl + NTT_B - 1) / NTT_B;
+                prof_select(*c, *sl, 2);
+                TRY(prof_mark(*sl, 0, s));
+                if (g_ntt_variant == 1) LAUNCH(ntt_pass_kernel_occ2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+                else LAUNCH(ntt_pass_kernel_lb0, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+                TRY(prof_mark(*sl, 1, s));
+                CU(cudaEventRecord(sl->xdev_ev, s));
+                return B200ZK_OK;
+            };
+            rc = phase1();
+            if (!bar.arrive(rc == B200ZK_OK)) { cudaStreamSynchronize(s); return rc != B200ZK_OK ? rc : fail(B200ZK_ERR_CUDA, "ntt: another GPU failed in the column pass"); }
+            // ---- phase 2: every peer has stored its part of my rows; row transforms, transposed store, strided copy down
+            auto phase2 = [&]() -> int32_t {
+                for (int h = 0; h < D; h++)
+                    if (h != g) CU(cudaStreamWaitEvent(s, leases[h].s->xdev_ev, 0));
+                NttExtra ex;
+                ex.out_final = OUT;
+                ex.t_out = 1 + (log_r - (uint32_t)__builtin_ctz((unsigned)D));
+                ex.out_scale = cos_out;
+                TRY(ntt_run(*c, *sl, sl->ntt_b.as<uint32_t>(), (uint32_t)Rl, log_c, omega2, B200ZK_NTT_MONT, nullptr, s, &ex));
+                if (io.host)
+                    CU(cudaMemcpy2DAsync(io.host + (size_t)g * Rl * 32, R * 32, OUT, Rl * 32, Rl * 32, C, cudaMemcpyDeviceToHost, s));
+                return B200ZK_OK;
+            };
+            rc = phase2();
+            cudaError_t e = cudaStreamSynchronize(s);
+            if (rc == B200ZK_OK && e != cudaSuccess) rc = fail(B200ZK_ERR_CUDA, std::string("ntt: ") + cudaGetErrorString(e));
+            // nobody reuses (or frees) a buffer its peers may still be writing or reading
+            bar.arrive(rc == B200ZK_OK);
+            return rc;
+        }});
+    }
+    return run_jobs(jobs);
+}
+
 int32_t ntt_host(const PolySrc& src, uint32_t batch, uint32_t log_n, const uint8_t omega[32], uint32_t flags, const uint8_t* coset_shift) {
     TRY(need_init());
     if ((!src.ptrs && !src.base) || !omega) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
@@ -1239,8 +1558,15 @@ int32_t ntt_host(const PolySrc& src, uint32_t batch, uint32_t log_n, const uint8
     if (src.ptrs)
         for (uint32_t j = 0; j < batch; j++)
             if (!src.ptrs[j]) return fail(B200ZK_ERR_INVALID_ARG, "null polynomial");
-    // independent polynomials: contiguous blocks per GPU, no exchange; each GPU's PCIe link carries its own block
     const int D = (int)g_devs.size();
+    static int shard_min_log = -1;
+    if (shard_min_log < 0) { const char* v = getenv("B200ZK_NTT_SHARD_MIN_LOG"); shard_min_log = v ? atoi(v) : 23; }
+    if (batch == 1 && D > 1 && !(D & (D - 1)) && (int)log_n >= shard_min_log) {
+        ShardIO io;
+        io.host = src.ptrs ? src.ptrs[0] : src.base;
+        return ntt_sharded(io, log_n, omega, flags, coset_shift);
+    }
+    // independent polynomials: contiguous blocks per GPU, no exchange; each GPU's PCIe link carries its own block
     int used = (int)std::min<uint32_t>(batch, (uint32_t)D);
     Ctx* first = nullptr;
     TRY(current_ctx(&first));
@@ -1573,6 +1899,8 @@ int32_t b200zk_shutdown(void) {
             if (kv.second.ninv) cudaFree(kv.second.ninv);
         }
         for (auto& kv : c.coset_tables) cudaFree(kv.second);
+        for (auto& kv : c.shard_plans) { cudaFree(kv.second.tw_local); cudaFree(kv.second.tw1); }
+        for (auto& kv : c.shard_cosets) cudaFree(kv.second);
         if (c.fixed_table) cudaFree(c.fixed_table);
         if (c.d_gen) cudaFree(c.d_gen);
         c.reg_stage.release();
@@ -1591,6 +1919,11 @@ int32_t b200zk_shutdown(void) {
             }
             if (sl.down_stream) cudaStreamDestroy(sl.down_stream);
             if (sl.ws_event) cudaEventDestroy(sl.ws_event);
+            if (sl.xdev_ev) cudaEventDestroy(sl.xdev_ev);
+            for (cudaEvent_t e : {sl.ev_fork, sl.ev_sorted, sl.ev_acc, sl.ev_done})
+                if (e) cudaEventDestroy(e);
+            if (sl.hi) cudaStreamDestroy(sl.hi);
+            if (sl.lo) cudaStreamDestroy(sl.lo);
             if (sl.stream) cudaStreamDestroy(sl.stream);
         }
         if (c.ws_event) cudaEventDestroy(c.ws_event);
@@ -1837,6 +2170,10 @@ static int32_t msm_dev_common(uint64_t bases, uint64_t offset, const void* d_sca
     if (!sh) return fail(B200ZK_ERR_INVALID_ARG, "msm: this slice of the table is not resident on the GPU that owns the scalars");
     DeviceScope ds(cp->ordinal);
     SlotLease lease(*cp);
+    if (!d_out_xyzz && batch >= 2)
+        return msm_run_batch(*cp, *lease.s, &sh->t, sh->t.d + 24 * (offset - sh->start), reinterpret_cast<const uint32_t*>(d_scalars), n,
+                             batch, scalar_fmt, reinterpret_cast<uint32_t*>(d_out_mont), reinterpret_cast<uint32_t*>(d_out_canon),
+                             reinterpret_cast<cudaStream_t>(stream), xa);
     return msm_run(*cp, *lease.s, &sh->t, sh->t.d + 24 * (offset - sh->start), reinterpret_cast<const uint32_t*>(d_scalars), n, batch,
                    scalar_fmt, reinterpret_cast<uint32_t*>(d_out_mont), reinterpret_cast<uint32_t*>(d_out_canon),
                    reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<uint32_t*>(d_out_xyzz), nullptr, xa);
@@ -2043,6 +2380,27 @@ int32_t b200zk_ntt_fr_batch_ptrs(uint8_t* const* data, uint32_t batch, uint32_t 
     PolySrc src;
     src.ptrs = data;
     return ntt_host(src, batch, log_n, omega, flags, coset_shift);
+}
+
+int32_t b200zk_ntt_sharded_layout(uint32_t log_n, uint32_t* out_log_r, uint32_t* out_log_c) {
+    TRY(need_init());
+    if (!out_log_r || !out_log_c) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    if (log_n > 32) return fail(B200ZK_ERR_INVALID_ARG, "ntt: log_n exceeds the 2-adicity of Fr");
+    ntt_shard_shape(log_n, (int)g_devs.size(), out_log_r, out_log_c);
+    return B200ZK_OK;
+}
+
+int32_t b200zk_ntt_fr_sharded_dev(void* const* d_in, void* const* d_out, uint32_t n_parts, uint32_t log_n, const uint8_t omega[32],
+                                  uint32_t flags, const uint8_t coset_shift[32]) {
+    TRY(need_init());
+    if (!d_in || !d_out || !omega) return fail(B200ZK_ERR_INVALID_ARG, "null pointer");
+    if (n_parts != g_devs.size()) return fail(B200ZK_ERR_INVALID_ARG, "ntt: one block per bound GPU");
+    for (uint32_t k = 0; k < n_parts; k++)
+        if (!d_in[k] || !d_out[k] || (((uintptr_t)d_in[k] | (uintptr_t)d_out[k]) & 15)) return fail(B200ZK_ERR_INVALID_ARG, "ntt: null or misaligned block");
+    ShardIO io;
+    io.d_in = d_in;
+    io.d_out = d_out;
+    return ntt_sharded(io, log_n, omega, flags, coset_shift);
 }
 
 int32_t b200zk_ntt_fr(uint8_t* data, uint32_t log_n, const uint8_t omega[32], uint32_t flags,

@@ -176,6 +176,32 @@ __global__ void __launch_bounds__(256) mb_femul_kernel(uint32_t* out, uint32_t i
     for (int k = 0; k < P::N; k++) s ^= x.l[k] ^ y.l[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// the arithmetic of one radix-2 DIF butterfly, (x, y) -> (x + y, (x - y) * w), four independent butterflies per thread like a
+// stage of the NTT kernel, with no memory traffic at all: what the integer pipes deliver for the butterfly alone, at the
+// occupancy the launch configuration allows (kind 13: 16 warps / SM like the NTT kernel, kind 14: 64 warps / SM)
+__global__ void __launch_bounds__(256, 2) mb_butterfly_kernel(uint32_t* out, uint32_t iters) {
+    Fr v[8], w = fe_one<FrParams>();
+#pragma unroll
+    for (int j = 0; j < 8; j++) { v[j] = fe_one<FrParams>(); v[j].l[0] += threadIdx.x + j; }
+    w.l[1] += blockIdx.x;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int q = 2; q >= 0; q--) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (j & (1 << q)) continue;
+                Fr x = v[j], y = v[j | (1 << q)];
+                v[j] = fe_add(x, y);
+                v[j | (1 << q)] = fe_mul(fe_sub(x, y), w);
+            }
+        }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        for (int k = 0; k < 8; k++) s ^= v[j].l[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 __global__ void __launch_bounds__(128) mb_madd_kernel(const uint32_t* gen_mont, uint32_t* out, uint32_t iters) {
     G1Affine q = g1a_ldg(gen_mont, 0);
     G1Xyzz acc;
@@ -227,7 +253,7 @@ int32_t b200zk_selftest_field(uint32_t field, uint32_t op, const uint8_t* a, con
 int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double* out_ops_per_s, double* out_ms) {
     ctx::Dev* d = nullptr;
     XTRY(ctx::current(&d));
-    if (kind > 11 || kind == 1 || !out_ops_per_s) return ctx::fail(B200ZK_ERR_INVALID_ARG, "bad microbench arguments");
+    if (kind > 14 || kind == 1 || !out_ops_per_s) return ctx::fail(B200ZK_ERR_INVALID_ARG, "bad microbench arguments");
     ctx::DeviceScope ds(ctx::ordinal(d));
     uint32_t* d_gen = nullptr;
     if (kind == 3) XTRY(ctx::generator_dev(d, &d_gen, ctx::stream(d)));
@@ -235,7 +261,7 @@ int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double* out_ops_per_s, 
     cudaStream_t s = ctx::stream(d);
     int sms = ctx::sm_count(d);
     unsigned threads = (kind == 3) ? 128 : 256;
-    unsigned blocks = (unsigned)sms * ((kind == 3) ? 3 : ((kind == 2) ? 4 : 8));
+    unsigned blocks = (unsigned)sms * ((kind == 3) ? 3 : ((kind == 2) ? 4 : ((kind == 12 || kind == 13) ? 2 : 8)));
     Scratch sc;
     XCU(cudaMalloc(&sc.p, (size_t)blocks * threads * 8 + 64));
     uint64_t* o64 = reinterpret_cast<uint64_t*>(sc.p);
@@ -274,6 +300,15 @@ int32_t b200zk_microbench(uint32_t kind, uint32_t iters, double* out_ops_per_s, 
             case 7:
                 XLAUNCH(mb_imad_cout_kernel, blocks, threads, 0, s, o64, iters, 12345u, 67890u);
                 per_thread = 24.0 * iters;
+                break;
+            case 12:   // Fr products at 16 warps / SM (the occupancy of the NTT kernel) instead of 64
+                XLAUNCH(mb_femul_kernel<FrParams>, blocks, threads, 0, s, o32, iters);
+                per_thread = 2.0 * iters;
+                break;
+            case 13:
+            case 14:   // butterflies per second
+                XLAUNCH(mb_butterfly_kernel, blocks, threads, 0, s, o32, iters);
+                per_thread = 12.0 * iters;
                 break;
             case 9:
                 XLAUNCH(mb_imad_parts_kernel<0>, blocks, threads, 0, s, o64, iters, 12345u, 67890u);

@@ -220,30 +220,33 @@ template <class P> HD Fe<P> fe_dbl(const Fe<P>& a) { return fe_add(a, a); }
 template <class P> HD void mont_mp_rows(uint32_t* E, uint32_t* O) {
     constexpr int N = P::N;
     uint32_t m;
-#ifdef __CUDA_ARCH__
-    // For M0 = 2^32 - 1 the quotient digit is -E[0].  Written as E[0] * M0 the compiler folds the negation into
-    // the products that follow and ptxas then emits every carry-chained m*p product as IMAD.X + IMAD.HI.U32.X
-    // (5 pipe cycles) instead of one IMAD.WIDE.U32.X (4); an opaque subtraction keeps the rows fused.
-    if (P::M0 == 0xffffffffu) asm volatile("sub.u32 %0, 0, %1;" : "=r"(m) : "r"(E[0]));
-    else m = E[0] * P::M0;
-#else
-    m = E[0] * P::M0;
-#endif
     if (P::LOW_LIMBS_TRIVIAL) {
-        uint32_t hi = m - (m != 0 ? 1u : 0u);
-        O[0] = add_cc(O[0], E[0]);             // 2^32 - m = E[0] (mod 2^32) because m = -E[0]
+        // For M0 = 2^32 - 1 the quotient digit is m = -E[0].  (Written as E[0] * M0 the compiler folds the negation into the
+        // products that follow and ptxas then emits every carry-chained m*p product as IMAD.X + IMAD.HI.U32.X, 5 pipe
+        // cycles, instead of one IMAD.WIDE.U32.X, 4; the opaque subtraction keeps the rows fused.)
+        // The product m * 0xffffffff = (m - c0) * 2^32 + (2^32 - m) with c0 = [m != 0]: the subtraction that forms m leaves
+        // exactly that borrow behind, so `hi` is one subtract-with-borrow, no compare / select.  A borrow may only feed a
+        // subtract and a carry only an add: PTX's flag after sub.cc is "not borrow" on the device (a + ~b + 1), so the two
+        // must not be mixed -- hence E[0] + m is formed by its own add, whose carry (again c0) enters the E row.
+        const uint32_t e0 = E[0];
+        m = sub_cc(0, e0);
+        const uint32_t hi = subc(m, 0);        // m - c0
+        E[0] = add_cc(e0, m);                  // = 0, carry c0
+        E[1] = addc_cc(E[1], 0);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], P::p(j), m, E[j], E[j + 1]);
+        O[N - 1] = addc(O[N - 1], 0);          // the carry that leaves E lands on O[N-1] (O is aligned one limb higher)
+        O[0] = add_cc(O[0], e0);               // 2^32 - m = E[0] (mod 2^32) because m = -E[0]
         O[1] = addc_cc(O[1], hi);
-    } else {
-        mad_wide_cc(O[0], O[1], P::p(1), m, O[0], O[1]);
+#pragma unroll
+        for (int k = 2; k < N; k += 2) madc_wide_cc(O[k], O[k + 1], P::p(k + 1), m, O[k], O[k + 1]);
+        return;
     }
+    m = E[0] * P::M0;
+    mad_wide_cc(O[0], O[1], P::p(1), m, O[0], O[1]);
 #pragma unroll
     for (int k = 2; k < N; k += 2) madc_wide_cc(O[k], O[k + 1], P::p(k + 1), m, O[k], O[k + 1]);
-    if (P::LOW_LIMBS_TRIVIAL) {
-        E[0] = add_cc(E[0], m);                // = 0, carry iff m != 0
-        E[1] = addc_cc(E[1], 0);
-    } else {
-        mad_wide_cc(E[0], E[1], P::p(0), m, E[0], E[1]);
-    }
+    mad_wide_cc(E[0], E[1], P::p(0), m, E[0], E[1]);
 #pragma unroll
     for (int j = 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], P::p(j), m, E[j], E[j + 1]);
     O[N - 1] = addc(O[N - 1], 0);

@@ -41,6 +41,14 @@ struct NttPassArgs {
     uint64_t total_cols;      // batch * n / R
     const uint32_t* scalar;   // multiply every output by *scalar (1/n of a single-pass inverse), or nullptr
     uint32_t reduce_in;       // canonical input may be >= r: reduce on read (transcript.ak:158-179)
+    // Multi-GPU four-step transform (b200zk.cu, ntt_sharded): the column pass of GPU g writes element (k1, i2) of the
+    // intermediate matrix straight into the HBM of the GPU that owns row k1 (peer store over NVLink) -- the only exchange of
+    // the transform is fused into this pass's store; the row pass writes its result transposed ([k2][k1]), which is the
+    // layout the strided D2H copy (or the resident caller) wants.
+    uint32_t scatter;         // 1: out element (u, k) goes to peer[k >> log_rl] + (((k & (2^log_rl - 1)) << log_c) + col0 + u)
+    uint32_t log_rl, log_c, col0;
+    uint32_t t_out;           // 0: off; else 1 + log2(batch): out element (poly, oi) goes to (oi << log2 batch) + poly
+    uint32_t* peer[16];
 };
 
 // Position of element e inside a word plane.  Layout 0: one pad word per 32 elements.  Layout 1 (WL): an XOR swizzle
@@ -109,9 +117,13 @@ struct FrMulCall {
 
 // radix-2 DIF stages on index bits lb+NB-1 .. lb of the CTA-local array; the thread owns the 8
 // elements whose index differs in bits lb..lb+2.
-template <int NB, class M, bool WL>
+// TWSM: the R/2 local twiddles were staged in shared memory (word planes like the data) by the caller, so a butterfly never
+// waits on a global load.  LB0: this is the sweep over index bits 0..NB-1, where the twiddle exponent of a butterfly depends
+// only on its position inside the thread (known at compile time): the multiplications by omega^0 disappear.
+template <int NB, class M, bool WL, bool TWSM = false, bool LB0 = false>
 __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restrict__ tw_local, uint32_t deg,
                                           uint32_t lb, uint32_t tid) {
+    if (LB0) lb = 0;
     uint32_t base;
     if (WL && lb + 2 <= 7) {
         // warp-local: warp w owns elements [256 w, 256 w + 256); the lane supplies the five index bits of 0..7 that the
@@ -144,12 +156,14 @@ __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restri
             Fr x = v[j], y = v[j | (1 << q)];
             v[j] = fe_add(x, y);
             Fr d = fe_sub(x, y);
-            if (q == 0 && lb == 0) {               // twiddle exponent is 0 on the last stage
+            if ((q == 0 && lb == 0) || (LB0 && (j & ((1 << q) - 1)) == 0)) {   // twiddle exponent is 0
                 v[j | (1 << q)] = d;
             } else {
                 uint32_t il = (base | ((uint32_t)j << lb)) & rmask;
                 uint32_t e = (il & ((1u << b) - 1)) << (deg - 1 - b);
-                v[j | (1 << q)] = M::mul(d, ntt_ldg(tw_local + 8 * (size_t)e));
+                if (LB0) e = (uint32_t)(j & ((1 << q) - 1)) << (deg - 1 - b);
+                Fr w = TWSM ? ntt_lds<false>(sm + 8 * NTT_PLANE, e) : ntt_ldg(tw_local + 8 * (size_t)e);
+                v[j | (1 << q)] = M::mul(d, w);
             }
         }
     }
@@ -157,11 +171,15 @@ __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restri
     for (int j = 0; j < 8; j++) ntt_sts<WL>(sm, base | ((uint32_t)j << lb), v[j]);
 }
 
-template <class M, bool WL>
+template <class M, bool WL, bool TWSM = false, bool LB0EN = TWSM>
 __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     extern __shared__ uint32_t sm[];
     const uint32_t tid = threadIdx.x;
     const uint32_t deg = a.deg;
+    if (TWSM && deg) {
+        // the R/2 local twiddles into planes 8..15 (visible after the barrier that follows the data load)
+        for (uint32_t e = tid; e < (1u << (deg - 1)); e += NTT_THREADS) ntt_sts<false>(sm + 8 * NTT_PLANE, e, ntt_ldg(a.tw_local + 8 * (size_t)e));
+    }
     const uint32_t logU = NTT_LOGB - deg;          // sub-transforms per CTA (log2)
     const uint64_t col0 = (uint64_t)blockIdx.x << logU;
     const uint64_t cmask = ((uint64_t)1 << a.log_cols) - 1;
@@ -206,9 +224,13 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     while (rem > 0) {
         int nb = rem >= 3 ? 3 : rem;
         uint32_t lb = (uint32_t)(rem - nb);
-        if (nb == 3) ntt_group<3, M, WL>(sm, a.tw_local, deg, lb, tid);
-        else if (nb == 2) ntt_group<2, M, WL>(sm, a.tw_local, deg, lb, tid);
-        else ntt_group<1, M, WL>(sm, a.tw_local, deg, lb, tid);
+        if (LB0EN && lb == 0) {
+            if (nb == 3) ntt_group<3, M, WL, TWSM, true>(sm, a.tw_local, deg, 0, tid);
+            else if (nb == 2) ntt_group<2, M, WL, TWSM, true>(sm, a.tw_local, deg, 0, tid);
+            else ntt_group<1, M, WL, TWSM, true>(sm, a.tw_local, deg, 0, tid);
+        } else if (nb == 3) ntt_group<3, M, WL, TWSM>(sm, a.tw_local, deg, lb, tid);
+        else if (nb == 2) ntt_group<2, M, WL, TWSM>(sm, a.tw_local, deg, lb, tid);
+        else ntt_group<1, M, WL, TWSM>(sm, a.tw_local, deg, lb, tid);
         rem -= nb;
         // the next sweep works on bits below lb: if both this sweep and the next stay inside a warp's 256-element block
         // the warp only has to wait for itself
@@ -234,9 +256,14 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
         uint64_t q = u & (((uint64_t)1 << a.log_s) - 1), p = u >> a.log_s;
         if (a.tw_pass) v = M::mul(v, ntt_ldg(a.tw_pass + 8 * ((p << deg) + k)));
         uint64_t oi = q + (((p << deg) + k) << a.log_s);
-        if (a.out_scale) v = M::mul(v, ntt_ldg(a.out_scale + 8 * oi));
+        if (a.scatter) {
+            ntt_st(a.peer[k >> a.log_rl] + 8 * ((((uint64_t)(k & ((1u << a.log_rl) - 1))) << a.log_c) + a.col0 + u), v);
+            continue;
+        }
+        uint64_t di = a.t_out ? ((oi << (a.t_out - 1)) + poly) : ((poly << a.log_n) + oi);
+        if (a.out_scale) v = M::mul(v, ntt_ldg(a.out_scale + 8 * (a.t_out ? di : oi)));
         if (a.scalar) v = M::mul(v, ntt_ldg(a.scalar));
-        ntt_st(a.out + 8 * ((poly << a.log_n) + oi), v);
+        ntt_st(a.out + 8 * di, v);
     }
 }
 
@@ -245,6 +272,11 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) { 
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_occ2(NttPassArgs a) { ntt_pass_body<FrMulInline, false>(a); }
 // swizzled planes, warp-local sweeps on the index bits 0..7 (CTA barriers only around the sweeps that cross warps)
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_wl2(NttPassArgs a) { ntt_pass_body<FrMulInline, true>(a); }
+// local twiddles staged in shared memory (a second set of word planes), compile-time exponents in the lowest sweep
+constexpr size_t NTT_SMEM_TW = (size_t)16 * NTT_PLANE * sizeof(uint32_t);
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_tw2(NttPassArgs a) { ntt_pass_body<FrMulInline, false, true>(a); }
+// compile-time exponents in the lowest sweep only (twiddles stay in global memory / L1)
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_lb0(NttPassArgs a) { ntt_pass_body<FrMulInline, false, false, true>(a); }
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_call2(NttPassArgs a) { ntt_pass_body<FrMulCall, false>(a); }
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_plain2(NttPassArgs a) { ntt_pass_body<FrMulPlain, false>(a); }
 __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel_call3(NttPassArgs a) { ntt_pass_body<FrMulCall, false>(a); }
@@ -263,6 +295,35 @@ __global__ void fr_powers_kernel(uint32_t* out, const uint32_t* base_p, const ui
         e = mult * p * k;
     }
     Fr acc = scale_p ? ntt_ld(scale_p) : fe_one<FrParams>();
+    while (e) {
+        if (e & 1) acc = fe_mul(acc, base);
+        base = fe_sqr(base);
+        e >>= 1;
+    }
+    ntt_st(out + 8 * i, acc);
+}
+
+// out[r * cols + c] = base^(offset + r * row_mul + c * col_mul): coset powers laid out like a GPU's slice of a sharded transform
+__global__ void fr_power_grid_kernel(uint32_t* out, const uint32_t* base_p, uint64_t rows, uint64_t cols, uint64_t row_mul,
+                                     uint64_t col_mul, uint64_t offset) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    uint64_t e = offset + (i / cols) * row_mul + (i % cols) * col_mul;
+    Fr base = ntt_ld(base_p), acc = fe_one<FrParams>();
+    while (e) {
+        if (e & 1) acc = fe_mul(acc, base);
+        base = fe_sqr(base);
+        e >>= 1;
+    }
+    ntt_st(out + 8 * i, acc);
+}
+// out[u * R + k] = scale * base^((u0 + u) * k): the twiddle block between the two steps of a four-step transform
+__global__ void fr_power_block_kernel(uint32_t* out, const uint32_t* base_p, const uint32_t* scale_p, uint64_t count, uint32_t deg,
+                                      uint64_t u0) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint64_t e = ((i >> deg) + u0) * (i & (((uint64_t)1 << deg) - 1));
+    Fr base = ntt_ld(base_p), acc = scale_p ? ntt_ld(scale_p) : fe_one<FrParams>();
     while (e) {
         if (e & 1) acc = fe_mul(acc, base);
         base = fe_sqr(base);

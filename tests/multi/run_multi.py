@@ -9,6 +9,8 @@ import os
 import sys
 import threading
 
+# one long transform is spread over the GPUs from 2^23 up; lowered so that the small sizes below take that path too
+os.environ.setdefault("B200ZK_NTT_SHARD_MIN_LOG", "13")
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -96,10 +98,22 @@ def main():
     capi.check(L.b200zk_msm_g1_dev(hr, 0, buf.ptr, n, 1, 0, None, dout.ptr, None))
     ok("_dev on the last GPU (replicated table)", dout.download(96) == want[3])
     rc = L.b200zk_msm_g1_dev(hs, 0, buf.ptr, n, 1, 0, None, dout.ptr, None)
-    ok("_dev against a slice that is not resident fails loudly", rc == -1)
+    ok("_dev against a slice that is not resident fails loudly", rc == (-1 if args.gpus > 1 else 0))
     capi.set_device(0)
     capi.check(L.b200zk_bases_release(hs))
     capi.check(L.b200zk_bases_release(hr))
+
+    # the verifier's ad-hoc sum (bases not resident), long enough to be split by point range over the GPUs
+    na = 20000
+    apts = orc.synth_bases(0xB600, 0, na)
+    asc = orc.synth_scalars(31, 0, na)
+    out = C.create_string_buffer(96)
+    capi.check(L.b200zk_msm_g1_adhoc(capi.addr(apts), 0, capi.addr(asc), 0, na, capi.addr(out)))
+    ok("ad-hoc sum of 20000 points over all GPUs", out.raw == orc.msm(apts, asc, na))
+    bad = bytearray(apts)
+    bad[96 * (na - 3)] ^= 1
+    rc = L.b200zk_msm_g1_adhoc(capi.addr(bytes(bad)), 0, capi.addr(asc), 0, na, capi.addr(out))
+    ok("ad-hoc sum rejects a bad point on the last GPU's slice", rc == -7)
 
     # NTT batch dealt out over the GPUs (contiguous and by pointer), against the oracle
     k = 12
@@ -113,6 +127,65 @@ def main():
     ptrs = (C.c_void_p * 5)(*[capi.addr(b) for b in bufs])
     capi.check(L.b200zk_ntt_fr_batch_ptrs(C.addressof(ptrs), 5, k, capi.addr(omega), 0, None))
     ok("ntt batch by pointer", [bytes(b) for b in bufs] == wantn)
+
+    # ONE transform over all GPUs (four-step, exchange fused into the column pass as peer stores): every flag combination at
+    # two sizes against the oracle, the BASELINE-adjacent size 2^23 forward, and the resident form with its block layouts
+    if args.gpus > 1:
+        R_MOD = zk.host.R_MOD
+        for kk in (13, 16, 20):
+            nn = 1 << kk
+            w = pow(zk.host.ROOT_OF_UNITY, 1 << (32 - kk), R_MOD)
+            wi = pow(w, R_MOD - 2, R_MOD)
+            data = orc.synth_scalars(70 + kk, 0, nn)
+            fb = lambda x: x.to_bytes(32, "little")
+            buf = bytearray(data)
+            capi.check(L.b200zk_ntt_fr(capi.addr(buf), kk, capi.addr(fb(w)), 0, None))
+            fwd = bytes(buf)
+            ok("sharded ntt 2^%d forward" % kk, fwd == orc.ntt(data, kk, fb(w)))
+            capi.check(L.b200zk_ntt_fr(capi.addr(buf), kk, capi.addr(fb(wi)), capi.NTT_INVERSE_SCALE, None))
+            ok("sharded ntt 2^%d inverse" % kk, bytes(buf) == data)
+            buf = bytearray(data)
+            capi.check(L.b200zk_ntt_fr(capi.addr(buf), kk, capi.addr(fb(w)), capi.NTT_COSET_IN, capi.addr(fb(7))))
+            cos = bytes(buf)
+            ok("sharded ntt 2^%d coset in" % kk, cos == orc.ntt(data, kk, fb(w), 0, fb(7)))
+            g7i = pow(7, R_MOD - 2, R_MOD)
+            capi.check(L.b200zk_ntt_fr(capi.addr(buf), kk, capi.addr(fb(wi)), capi.NTT_INVERSE_SCALE | capi.NTT_COSET_OUT, capi.addr(fb(g7i))))
+            ok("sharded ntt 2^%d coset out" % kk, bytes(buf) == data)
+        kk = 16
+        nn = 1 << kk
+        lr, lc = C.c_uint32(0), C.c_uint32(0)
+        capi.check(L.b200zk_ntt_sharded_layout(kk, C.byref(lr), C.byref(lc)))
+        Rr, Cc = 1 << lr.value, 1 << lc.value
+        Cl, Rl = Cc // args.gpus, Rr // args.gpus
+        w = pow(zk.host.ROOT_OF_UNITY, 1 << (32 - kk), R_MOD)
+        data = orc.synth_scalars(99, 0, nn)
+        want = orc.ntt(data, kk, w.to_bytes(32, "little"))
+        import numpy as np
+        x = np.frombuffer(data, dtype=np.uint8).reshape(Rr, Cc, 32)
+        ins, outs = [], []
+        for g in range(args.gpus):
+            capi.set_device(g)
+            blk = np.ascontiguousarray(x[:, g * Cl:(g + 1) * Cl, :]).tobytes()
+            b_in = zk.host.DeviceBuffer(len(blk))
+            b_in.upload(blk)
+            ins.append(b_in)
+            outs.append(zk.host.DeviceBuffer(len(blk)))
+        capi.set_device(0)
+        pin = (C.c_void_p * args.gpus)(*[b.ptr for b in ins])
+        pout = (C.c_void_p * args.gpus)(*[b.ptr for b in outs])
+        capi.check(L.b200zk_ntt_fr_sharded_dev(C.addressof(pin), C.addressof(pout), args.gpus, kk, capi.addr(w.to_bytes(32, "little")), 0, None))
+        y = np.zeros((Cc, Rr, 32), dtype=np.uint8)            # X[k1 + R k2] at [k2][k1]
+        for g in range(args.gpus):
+            capi.set_device(g)
+            y[:, g * Rl:(g + 1) * Rl, :] = np.frombuffer(outs[g].download(), dtype=np.uint8).reshape(Cc, Rl, 32)
+        capi.set_device(0)
+        ok("sharded ntt resident form (block layouts)", y.tobytes() == want)
+        kk = 23
+        data = orc.synth_scalars(5, 0, 1 << kk)
+        w = pow(zk.host.ROOT_OF_UNITY, 1 << (32 - kk), R_MOD).to_bytes(32, "little")
+        buf = bytearray(data)
+        capi.check(L.b200zk_ntt_fr(capi.addr(buf), kk, capi.addr(w), 0, None))
+        ok("sharded ntt 2^23 forward vs oracle", bytes(buf) == orc.ntt(data, kk, w))
 
     # a larger sharded MSM in full against the oracle, and one by the discrete-log identity
     nb = 1 << args.big_log_n

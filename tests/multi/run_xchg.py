@@ -51,7 +51,12 @@ def main():
         checks["%s no timeout" % mode] = not m.timed_out()
         m.close()
     dist.barrier()
-    print(json.dumps({"rank": rank, "ok": all(checks.values()), "checks": checks}), flush=True)
+    res = json.dumps({"rank": rank, "ok": all(checks.values()), "checks": checks})
+    outdir = os.environ.get("XCHG_OUT")
+    if outdir:                                     # one file per rank: the ranks' stdout lines may interleave
+        with open(os.path.join(outdir, "rank%d.json" % rank), "w") as f:
+            f.write(res)
+    print(res, flush=True)
     dist.destroy_process_group()
     return 0 if all(checks.values()) else 1
 

@@ -121,7 +121,11 @@ def test_cpp_header_mirror_compiles_and_fails_loudly(zk):
         '    using namespace b200zk;\n'
         '    try { init(); } catch (const Error& e) { return e.code == B200ZK_ERR_NO_DEVICE ? 42 : 1; }\n'
         '    DeviceFr v(std::vector<Fr>(8)); auto q = poly::kate_div(v, Fr{}); (void)q;\n'
-        '    Fr s{}; s[0] = 5; Fr w{}; w[0] = 1; auto pk = ParamsKZG::unsafe_setup(0, s, w); (void)pk; return 0;\n'
+        '    Fr s{}; s[0] = 5; Fr w{}; w[0] = 1; auto pk = ParamsKZG::unsafe_setup(0, s, w);\n'
+        '    Transcript t; t.common_scalar(s); std::vector<const DeviceFr*> ps{&v}; std::vector<ProverQuery> qs{{0, s}};\n'
+        '    auto proof = multi_open(pk, t, ps, qs); Transcript t2; t2.common_scalar(s);\n'
+        '    std::vector<const std::vector<Fr>*> cols; auto cs = KZGCommitmentScheme::commit_batch(pk, cols); (void)cs;\n'
+        '    auto g = multi_prepare(t2, {G1Compressed{}}, {VerifierQuery{0, s, s}}, proof); auto lr = g.eval(); (void)lr; return 0;\n'
         '}\n')
     libdir = os.path.join(ROOT, "plutus-halo2-verifier-gen_b200")
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", libdir, "-lb200zk",

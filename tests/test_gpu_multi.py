@@ -36,10 +36,13 @@ def test_multi_process_peer_exchange(world):
     rank ends up with the oracle's result, for device-resident and host-buffer calls."""
     if _gpus() < world:
         pytest.skip("needs %d GPUs" % world)
+    import tempfile
     port = 29600 + os.getpid() % 300
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-                          "--master-addr", "127.0.0.1", "--master-port", str(port),
-                          os.path.join(ROOT, "tests", "multi", "run_xchg.py")], capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
-    assert lines and all(l["ok"] for l in lines)
+    with tempfile.TemporaryDirectory() as tmp:
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                              "--master-addr", "127.0.0.1", "--master-port", str(port),
+                              os.path.join(ROOT, "tests", "multi", "run_xchg.py")], capture_output=True, text=True, timeout=900,
+                             env=dict(os.environ, XCHG_OUT=tmp))
+        assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+        res = [json.load(open(os.path.join(tmp, "rank%d.json" % r))) for r in range(world)]
+    assert all(r["ok"] for r in res), res
