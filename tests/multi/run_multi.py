@@ -137,19 +137,19 @@ def main():
             w = pow(zk.host.ROOT_OF_UNITY, 1 << (32 - kk), R_MOD)
             wi = pow(w, R_MOD - 2, R_MOD)
             data = orc.synth_scalars(70 + kk, 0, nn)
-            fb = lambda x: x.to_bytes(32, "little")
+            # (byte strings passed by address are kept in named variables so that they outlive the call)
+            wb, wib, g7, g7i = (x.to_bytes(32, "little") for x in (w, wi, 7, pow(7, R_MOD - 2, R_MOD)))
             buf = bytearray(data)
-            capi.check(L.b200zk_ntt_fr(capi.addr(buf), kk, capi.addr(fb(w)), 0, None))
+            capi.check(L.b200zk_ntt_fr(capi.addr(buf), kk, capi.addr(wb), 0, None))
             fwd = bytes(buf)
-            ok("sharded ntt 2^%d forward" % kk, fwd == orc.ntt(data, kk, fb(w)))
-            capi.check(L.b200zk_ntt_fr(capi.addr(buf), kk, capi.addr(fb(wi)), capi.NTT_INVERSE_SCALE, None))
+            ok("sharded ntt 2^%d forward" % kk, fwd == orc.ntt(data, kk, wb))
+            capi.check(L.b200zk_ntt_fr(capi.addr(buf), kk, capi.addr(wib), capi.NTT_INVERSE_SCALE, None))
             ok("sharded ntt 2^%d inverse" % kk, bytes(buf) == data)
             buf = bytearray(data)
-            capi.check(L.b200zk_ntt_fr(capi.addr(buf), kk, capi.addr(fb(w)), capi.NTT_COSET_IN, capi.addr(fb(7))))
+            capi.check(L.b200zk_ntt_fr(capi.addr(buf), kk, capi.addr(wb), capi.NTT_COSET_IN, capi.addr(g7)))
             cos = bytes(buf)
-            ok("sharded ntt 2^%d coset in" % kk, cos == orc.ntt(data, kk, fb(w), 0, fb(7)))
-            g7i = pow(7, R_MOD - 2, R_MOD)
-            capi.check(L.b200zk_ntt_fr(capi.addr(buf), kk, capi.addr(fb(wi)), capi.NTT_INVERSE_SCALE | capi.NTT_COSET_OUT, capi.addr(fb(g7i))))
+            ok("sharded ntt 2^%d coset in" % kk, cos == orc.ntt(data, kk, wb, 0, g7))
+            capi.check(L.b200zk_ntt_fr(capi.addr(buf), kk, capi.addr(wib), capi.NTT_INVERSE_SCALE | capi.NTT_COSET_OUT, capi.addr(g7i)))
             ok("sharded ntt 2^%d coset out" % kk, bytes(buf) == data)
         kk = 16
         nn = 1 << kk
@@ -173,7 +173,8 @@ def main():
         capi.set_device(0)
         pin = (C.c_void_p * args.gpus)(*[b.ptr for b in ins])
         pout = (C.c_void_p * args.gpus)(*[b.ptr for b in outs])
-        capi.check(L.b200zk_ntt_fr_sharded_dev(C.addressof(pin), C.addressof(pout), args.gpus, kk, capi.addr(w.to_bytes(32, "little")), 0, None))
+        wb = w.to_bytes(32, "little")
+        capi.check(L.b200zk_ntt_fr_sharded_dev(C.addressof(pin), C.addressof(pout), args.gpus, kk, capi.addr(wb), 0, None))
         y = np.zeros((Cc, Rr, 32), dtype=np.uint8)            # X[k1 + R k2] at [k2][k1]
         for g in range(args.gpus):
             capi.set_device(g)

@@ -161,9 +161,14 @@ def run_circuit(zk, lib, L, name, reps=3, check_all=False, threads=0):
             t0 = time.perf_counter()
             L.orc_g1_msm(bases.ctypes.data, col.ctypes.data, n, o.ctypes.data, threads)
             tt.append(time.perf_counter() - t0)
-        rec["parity_first_commitment"] = None
-        L.orc_g1_msm(bases.ctypes.data, cols[0].ctypes.data, n, o.ctypes.data, 0)
-        rec["parity_first_commitment"] = bytes(out[:96].numpy()) == bytes(o)
+        checked = range(ncom) if check_all else (0,)
+        good = True
+        for j in checked:
+            L.orc_g1_msm(bases.ctypes.data, cols[j].ctypes.data, n, o.ctypes.data, threads)
+            good = good and bytes(out[96 * j:96 * j + 96].numpy()) == bytes(o)
+        rec["parity_commitments_checked"] = len(checked)
+        rec["parity"] = good
+        assert good, "a commitment of the %s trace differs from the CPU checker" % name
         cpu_msm = tt[0] * (ncom - nuni) + tt[1] * nuni
         buf = cols[-1].copy()
         t0 = time.perf_counter()
