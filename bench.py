@@ -465,9 +465,10 @@ def main():
                          "fixed_accounting_note": "SURVEY 8d's size-independent accounting (48 000 limb-MACs/point = 16 windows x 10 products x 300) / "
                                                   "accumulate time / peak; exceeds 1 because window tables need only %d rows and the additions are "
                                                   "cheaper than 10 plain products -- a comparison figure, not a utilisation" % rows,
-                         "traffic": ncu_traffic("r01_ncu_msm_accumulate_2p24.json", 1) if (args.log_n == 24 and world == 1) else None,
-                         "traffic_source": "static_profile: profiles/r01_ncu_msm_accumulate_2p24.json (ncu --set full capture of this command at "
-                                           "commit 246bfb6), not measured in this run",
+                         "traffic": ncu_traffic("r02_ncu_msm_acc.json", 1) if (args.log_n == 24 and world == 1) else None,
+                         "traffic_source": "static_profile: profiles/r02_ncu_msm_acc.json (dram__bytes_read.sum + dram__bytes_write.sum of one launch, "
+                                           "ncu --set full capture of `bench.py --steps 3 --warmup 3 --no-cpu --no-circuits`, tools/profile_round.sh), "
+                                           "not measured in this run",
                          "algorithmic_bytes": 100.0 * n_local * rows,
                          "window_bits": prof.get("window_bits"), "table_rows": rows,
                          "phases_ms": {"sort": sort_ms, "accumulate": acc_ms, "tail": tail_ms},
@@ -534,7 +535,16 @@ def bench_single_process(zk, lib, torch, np, args, n_gpus, expect):
     assert ok_host and ok_res, "single-process multi-GPU result differs from the per-rank path"
     del slices, h_sc
     ntt = bench_sharded_ntt(zk, lib, torch, np, args, n_gpus) if (n_gpus & (n_gpus - 1)) == 0 and not args.no_ntt else None
-    return {"n_gpus": n_gpus, "ntt_sharded": ntt, "e2e_single_process": {"value": n / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
+    # a proof's columns over the GPUs: the host-buffer route of the atms k = 19 trace (18 commitments as one pointer-less batch
+    # call, 15 + 15 + 1 transforms as batch calls) with all N GPUs bound -- tables replicated, columns dealt out, no exchange
+    proof = None
+    if not args.no_circuits:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import circuit_bench
+        rec = circuit_bench.run_circuit(zk, lib, None, "atms19", 3, False, 0)
+        proof = {k: rec[k] for k in ("circuit", "k", "commitments", "ntt_columns", "gpu_trace_ms", "gpu_msm_ms", "gpu_ntt_ms")}
+        proof["note"] = "host buffers in and out, host clock; compare with circuits.traces[atms19].gpu_trace_ms of the 1-GPU line"
+    return {"n_gpus": n_gpus, "ntt_sharded": ntt, "proof_columns_over_gpus": proof, "e2e_single_process": {"value": n / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
                                                      "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 96},
             "resident_single_process": {"value": n / (res_ms * 1e-3), "unit": "points/s", "ms_per_step": res_ms},
             "table_build_ms": build_ms, "parity_with_per_rank_path": True,
@@ -636,7 +646,8 @@ def bench_ntt(zk, lib, torch, np, args, stream, imad_peak):
         "e2e": {"value": n / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n,
                 "ms_per_step": e2e_s * 1e3},
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                     "traffic": ncu_traffic("r01_ncu_ntt_pass_2p22.json", 2) if log_n == 22 else None,
+                     "traffic": ncu_traffic("r02_ncu_ntt.json", 2) if log_n == 22 else None,
+                     "traffic_source": "static_profile: profiles/r02_ncu_ntt.json (both passes of one 2^22 transform), not measured in this run",
                      "imad": {"achieved_t_imad_wide_s": issued / (ms * 1e-3) / 1e12, "peak_t_imad_wide_s": imad_peak / 1e12,
                               "frac": (issued / (ms * 1e-3)) / imad_peak if imad_peak else None,
                               "frac_fixed_accounting": (lmacs / (ms * 1e-3)) / imad_peak if imad_peak else None,

@@ -298,7 +298,9 @@ Ctx* g_prof_ctx = nullptr;
 Slot* g_prof_slot = nullptr;
 int g_ntt_variant = 7;            // 7: two CTAs per SM, compile-time twiddle exponents in the lowest sweep (default); 1: without them;
                                   // 0: one CTA per SM; 2..6 experiments.  B200ZK_NTT_VARIANT overrides.
-int64_t g_chunk_min = 1ll << 23;  // a single host-buffer MSM of at least this many points streams its scalars in two pieces
+int64_t g_chunk_min = 1ll << 20;  // a single host-buffer MSM of at least this many points streams its scalars in two pieces
+                                  // (measured end to end, pinned scalars: 2^21 12.38 -> 11.72 ms, 2^22 23.02 -> 21.33 ms; this is also what
+                                  // each GPU of a sharded 2^24 MSM does with its 2^21..2^23-point slice)
 size_t g_batch_stream_min = (size_t)128 << 20;
 int64_t g_ntt_pipe_min = 32ll << 20;
 int g_scatter_passes_env = 0;
@@ -776,8 +778,9 @@ int32_t msm_run(Ctx& c, Slot& sl, const BaseTable* tab, const uint32_t* d_bases,
         if (serial)
             LAUNCH(msm_reduce_kernel, (unsigned)((groups + 63) / 64), 64, 0, s, S_in, A_in, S_out, A_out, m, m_out,
                    (uint32_t)nwin, scale_log);
-        else if (groups <= 600)
-            // top of the tree: one CTA per group, 8 lanes per node, additions in 4 product levels instead of 14 products
+        else if (groups <= 1184)
+            // top of the tree (up to one full wave of 256-thread CTAs): one CTA per group, 8 lanes per node, additions in 4
+            // product levels instead of 14 products
             LAUNCH(msm_reduce_coop8_kernel, (unsigned)groups, 256, 0, s, S_in, A_in, S_out, A_out, m, m_out, (uint32_t)nwin, scale_log);
         else
             LAUNCH(msm_reduce_coop_kernel, (unsigned)((groups + 3) / 4), 128, 0, s, S_in, A_in, S_out, A_out, m, m_out,

@@ -13,7 +13,7 @@ Batches of independent polynomials are split by :func:`split_batch` with no coll
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 from . import capi
 from .capi import check, lib
@@ -142,100 +142,49 @@ def combine_partials_host(partials: List[bytes]) -> bytes:
 
 
 # ------------------------------------------------------------------------------------------------
-# One large NTT over the GPUs of a node (worth it at 2^23..2^24 because the transform is
-# bound by the integer pipe, not by the exchange): four-step decomposition n = R * C,
+# One large NTT over the GPUs of a node.  The transform itself runs inside the library from ONE process
+# (b200zk_init_devices + b200zk_ntt_fr / b200zk_ntt_fr_sharded_dev; csrc/b200zk.cu, ntt_sharded): four-step decomposition
+# n = R * C,
 #   X[k1 + R k2] = sum_{i2} (w^R)^(i2 k2) * w^(i2 k1) * sum_{i1} (w^C)^(i1 k1) x[i1 C + i2],
-# natural order in and out, block-distributed (rank g holds elements [g n/G, (g+1) n/G)).
-#   a2a #1 : row blocks -> column blocks          (each rank gets all i1 for its i2 block)
-#   local  : C/G transforms of length R, times the twiddle block w^(i2 k1)   (b200zk_ntt_fr_dev, _fr_pointwise_dev)
-#   a2a #2 : -> all i2 for the rank's k1 block
-#   local  : R/G transforms of length C
-#   a2a #3 : back to natural order (k = k2 R + k1: the rank's k2 block, all k1)
-# Each exchange moves n/G elements per rank over NVLink (64 MiB at 2^24 on 8 GPUs); packing is a strided copy.
+# GPU g transforming the columns i2 in [g C/G, (g+1) C/G), storing row k1 of the twiddled intermediate matrix straight into
+# the HBM of the GPU that owns it (the one exchange, peer stores from inside the kernel), then every GPU transforming its R/G
+# rows.  What lives here is the plan's host-side mirror -- shapes, block layouts, who owns what -- for callers of the
+# resident form and for the CPU tests of the decomposition (tests/test_dist_gloo.py).
 # ------------------------------------------------------------------------------------------------
-class GpuNttOps:
-    """The per-rank primitives of :class:`ShardedNTT` on libb200zk.so (device tensors, torch's current stream)."""
+class FourStepPlan:
+    """Shapes and index maps of the multi-GPU transform (mirror of ``ntt_shard_shape`` / ``ntt_sharded`` in csrc/b200zk.cu)."""
 
-    def __init__(self):
-        import torch
+    MAX_LOG_R = 11          # the column transforms run in one pass of the NTT kernel
 
-        self.torch = torch
-
-    def _stream(self):
-        return self.torch.cuda.current_stream().cuda_stream
-
-    def ntt_batch(self, t, batch: int, log_len: int, omega: int, inverse: bool) -> None:
-        from .host import fr_bytes
-
-        om = fr_bytes(omega)
-        flags = capi.NTT_INVERSE_SCALE if inverse else 0
-        check(lib().b200zk_ntt_fr_dev(t.data_ptr(), batch, log_len, capi.addr(om), flags, None, self._stream()))
-
-    def power_table(self, base: int, row0: int, rows: int, cols: int, device):
-        from .host import fr_bytes
-
-        t = self.torch.empty(rows * cols * 32, dtype=self.torch.uint8, device=device)
-        bb = fr_bytes(base)
-        check(lib().b200zk_fr_power_table_dev(capi.addr(bb), row0, rows, cols, t.data_ptr(), self._stream()))
-        return t
-
-    def mul_table(self, t, table) -> None:
-        """t[i] *= table[i]; t canonical, table in Montgomery form (so the product is canonical again)."""
-        check(lib().b200zk_fr_pointwise_dev(0, t.data_ptr(), table.data_ptr(), None, t.data_ptr(), t.numel() // 32, self._stream()))
-
-
-class ShardedNTT:
-    """Rank-local state of one forward or inverse NTT of 2^log_n elements over `world` ranks."""
-
-    def __init__(self, log_n: int, omega: int, rank: int, world: int, group=None, inverse: bool = False, ops=None, modulus: Optional[int] = None):
-        import torch
-
-        from .host import R_MOD
-
-        self.torch = torch
-        self.p = modulus or R_MOD
-        if world & (world - 1):
-            raise ValueError("world size must be a power of two")
-        log_g = world.bit_length() - 1
-        self.log_r = max(log_n // 2, log_g)
+    def __init__(self, log_n: int, parts: int):
+        if parts < 2 or parts & (parts - 1):
+            raise ValueError("a sharded transform needs 2, 4, 8 or 16 GPUs")
+        log_g = parts.bit_length() - 1
+        self.log_n, self.parts = log_n, parts
+        self.log_r = min(self.MAX_LOG_R, log_n - log_g)
         self.log_c = log_n - self.log_r
-        if self.log_c < log_g:
-            raise ValueError("transform too small for this many ranks")
-        self.log_n, self.omega, self.rank, self.world, self.group, self.inverse = log_n, omega % self.p, rank, world, group, inverse
-        self.ops = ops or GpuNttOps()
-        self.R, self.Cc = 1 << self.log_r, 1 << self.log_c
-        self.Rl, self.Cl = self.R // world, self.Cc // world
-        self.table = None
+        self.R, self.C = 1 << self.log_r, 1 << self.log_c
+        if self.R < parts or self.C < parts:
+            raise ValueError("transform too small to shard over %d GPUs" % parts)
+        self.Rl, self.Cl = self.R // parts, self.C // parts
 
-    def _a2a(self, send):
-        recv = self.torch.empty_like(send)
-        if self.world == 1:
-            recv.copy_(send)
-        else:
-            self.torch.distributed.all_to_all_single(recv, send, group=self.group)
-        return recv
+    def block_in(self, x: Sequence, g: int) -> List[List]:
+        """GPU g's input block [R][C/G] of a natural-order vector: x[i1 * C + g * Cl + u]."""
+        return [[x[i1 * self.C + g * self.Cl + u] for u in range(self.Cl)] for i1 in range(self.R)]
 
-    def run(self, x_local):
-        """x_local: uint8 tensor of (n / world) * 32 bytes, this rank's contiguous slice in natural order (canonical
-        or Montgomery Fr; the transform is linear).  Returns the rank's slice of the result, same layout."""
-        G, R, Cc, Rl, Cl = self.world, self.R, self.Cc, self.Rl, self.Cl
-        w = self.omega
-        if self.table is None:   # w^((rank*Cl + u) * k1), laid out like the data it multiplies: [u][k1]
-            self.table = self.ops.power_table(w, self.rank * Cl, Cl, R, x_local.device)
-        # 32-byte elements are moved as pairs of 16-byte words (complex128 is only a container type here)
-        W16 = self.torch.complex128
-        x = x_local.view(W16).view(Rl, G, Cl, 2)
-        # a2a #1: [Rl][G][Cl] -> send [G][Rl][Cl]; receive rows of every source rank: [R][Cl]
-        a = self._a2a(x.permute(1, 0, 2, 3).contiguous())
-        # local: [R][Cl] -> [Cl][R], transforms over i1 with root w^C, then the twiddle block
-        y = a.view(R, Cl, 2).permute(1, 0, 2).contiguous()
-        self.ops.ntt_batch(y.view(-1).view(self.torch.uint8), Cl, self.log_r, pow(w, Cc, self.p), self.inverse)
-        self.ops.mul_table(y.view(-1).view(self.torch.uint8), self.table)
-        # a2a #2: [Cl][G][Rl] -> send [G][Cl][Rl]; receive [C][Rl]
-        b = self._a2a(y.view(Cl, G, Rl, 2).permute(1, 0, 2, 3).contiguous())
-        # local: [C][Rl] -> [Rl][C], transforms over i2 with root w^R
-        z = b.view(Cc, Rl, 2).permute(1, 0, 2).contiguous()
-        self.ops.ntt_batch(z.view(-1).view(self.torch.uint8), Rl, self.log_c, pow(w, R, self.p), self.inverse)
-        # a2a #3: z[k1_local][k2] -> natural order k = k2 R + k1: send [G][Rl][Cl], receive [R][Cl] -> [Cl][R]
-        c = self._a2a(z.view(Rl, G, Cl, 2).permute(1, 0, 2, 3).contiguous())
-        return c.view(R, Cl, 2).permute(1, 0, 2).contiguous().view(-1).view(self.torch.uint8)
+    def twiddle_exponent(self, g: int, u: int, k1: int) -> int:
+        """The column pass of GPU g multiplies output k1 of its column u by w^this."""
+        return (g * self.Cl + u) * k1
+
+    def row_owner(self, k1: int) -> Tuple[int, int]:
+        """(GPU that runs the row transform of row k1, row index inside its block)."""
+        return k1 // self.Rl, k1 % self.Rl
+
+    def natural_from_blocks_out(self, blocks: Sequence[Sequence[Sequence]]) -> List:
+        """Natural-order result from the per-GPU output blocks [C][R/G]: block h holds X[h * Rl + k1 + R * k2] at [k2][k1]."""
+        out = [None] * (1 << self.log_n)
+        for h, blk in enumerate(blocks):
+            for k2 in range(self.C):
+                for k1 in range(self.Rl):
+                    out[h * self.Rl + k1 + self.R * k2] = blk[k2][k1]
+        return out

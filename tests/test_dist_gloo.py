@@ -65,45 +65,10 @@ def test_point_range_sharding_world2(oracle):
     assert got[0] == got[1] == full
 
 
-class _CpuNttOps:
-    """Stands in for the per-GPU kernels in the gloo test of the sharded NTT: the checker's transforms on CPU tensors."""
-
-    def __init__(self, pyref):
-        self.P = pyref
-
-    @staticmethod
-    def _ints(t):
-        b = bytes(t.contiguous().view(-1).numpy())
-        return [int.from_bytes(b[32 * i:32 * i + 32], "little") for i in range(len(b) // 32)]
-
-    @staticmethod
-    def _store(t, vals):
-        import torch
-        raw = b"".join(v.to_bytes(32, "little") for v in vals)
-        t.view(-1).copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
-
-    def ntt_batch(self, t, batch, log_len, omega, inverse):
-        vals, n = self._ints(t), 1 << log_len
-        out = []
-        for b in range(batch):
-            r = self.P.ntt(vals[b * n:(b + 1) * n], omega)
-            if inverse:
-                ninv = self.P.fr_inv(n)
-                r = [v * ninv % self.P.R_MOD for v in r]
-            out += r
-        self._store(t, out)
-
-    def power_table(self, base, row0, rows, cols, device):
-        import torch
-        t = torch.empty(rows * cols * 32, dtype=torch.uint8)
-        self._store(t, [pow(base, (row0 + r) * c, self.P.R_MOD) for r in range(rows) for c in range(cols)])
-        return t
-
-    def mul_table(self, t, table):
-        self._store(t, [a * b % self.P.R_MOD for a, b in zip(self._ints(t), self._ints(table))])
-
-
-def _ntt_worker(rank, world, port, log_n, inverse, q):
+def _four_step_worker(rank, world, port, log_n, q):
+    """One rank of the multi-GPU transform with the checker's transforms standing in for the kernels and gloo's all_to_all for the
+    peer stores: column block in, column transforms with root w^C, twiddles w^((g Cl + u) k1), every row k1 sent to its owner,
+    row transforms with root w^R, transposed output block."""
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
@@ -114,51 +79,68 @@ def _ntt_worker(rank, world, port, log_n, inverse, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     n = 1 << log_n
-    full = [P.splitmix64(1000 + i) * P.splitmix64(7 + i) % P.R_MOD for i in range(n)]
-    s, e = zdist.shard_range(n, rank, world)
-    mine = torch.frombuffer(bytearray(b"".join(v.to_bytes(32, "little") for v in full[s:e])), dtype=torch.uint8)
+    x = [P.splitmix64(17 * i + 3) % P.R_MOD for i in range(n)]
     w = P.omega(log_n)
-    if inverse:
-        w = P.fr_inv(w)
-    plan = zdist.ShardedNTT(log_n, w, rank, world, inverse=inverse, ops=_CpuNttOps(P))
-    out = plan.run(mine)
-    q.put((rank, bytes(out.numpy())))
+    plan = zdist.FourStepPlan(log_n, world)
+    blk = plan.block_in(x, rank)                                   # [R][Cl]
+    wR, wC = pow(w, plan.R, P.R_MOD), pow(w, plan.C, P.R_MOD)
+    cols = []
+    for u in range(plan.Cl):                                       # column transforms + twiddles
+        y = P.ntt([blk[i1][u] for i1 in range(plan.R)], wC)
+        cols.append([y[k1] * pow(w, plan.twiddle_exponent(rank, u, k1), P.R_MOD) % P.R_MOD for k1 in range(plan.R)])
+    # the exchange: rows k1 of block h go to rank h, as [Rl][Cl] (what the column pass stores into its peer's HBM)
+    def pack(vals):
+        return torch.frombuffer(bytearray(b"".join(v.to_bytes(32, "little") for v in vals)), dtype=torch.uint8)
+    send = [pack([cols[u][h * plan.Rl + r] for r in range(plan.Rl) for u in range(plan.Cl)]) for h in range(world)]
+    # (gloo has no all_to_all: everybody gathers everybody's send list and keeps the piece addressed to it)
+    mine = torch.cat(send)
+    everyone = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(everyone, mine)
+    seg = send[0].numel()
+    recv = [everyone[g][rank * seg:(rank + 1) * seg] for g in range(world)]
+    rows = [[0] * plan.C for _ in range(plan.Rl)]
+    for g in range(world):
+        b = bytes(recv[g].numpy())
+        for r in range(plan.Rl):
+            for u in range(plan.Cl):
+                o = 32 * (r * plan.Cl + u)
+                rows[r][g * plan.Cl + u] = int.from_bytes(b[o:o + 32], "little")
+        assert all(plan.row_owner(rank * plan.Rl + r) == (rank, r) for r in range(plan.Rl))
+    z = [P.ntt(rows[r], wR) for r in range(plan.Rl)]               # row transforms
+    out_blk = [[z[r][k2] for r in range(plan.Rl)] for k2 in range(plan.C)]   # transposed store: [C][Rl]
+    q.put((rank, out_blk))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("log_n,inverse,world", [(6, False, 2), (7, False, 2), (7, True, 2), (8, False, 4)])
-def test_sharded_ntt_world2(pyref, log_n, inverse, world):
-    """The exchange / transpose / twiddle logic of dist.ShardedNTT on two (and four) gloo ranks, with the checker's
-    transforms standing in for the kernels: the concatenated result equals the checker's transform of the whole vector."""
+@pytest.mark.parametrize("log_n,world", [(6, 2), (9, 2), (8, 4)])
+def test_four_step_plan_over_gloo_ranks(pyref, zk, log_n, world):
+    """The decomposition the multi-GPU transform implements (csrc/b200zk.cu, ntt_sharded; mirrored by dist.FourStepPlan): block
+    layouts, twiddle exponents, row ownership and the transposed output reproduce the plain transform."""
     import torch.multiprocessing as mp
-    port = 29617 + (os.getpid() + log_n + 7 * inverse + 13 * world) % 1000
+    zdist = importlib.import_module("plutus-halo2-verifier-gen_b200.dist")
+    port = 29700 + os.getpid() % 200 + log_n
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_ntt_worker, args=(r, world, port, log_n, inverse, q)) for r in range(world)]
+    procs = [ctx.Process(target=_four_step_worker, args=(r, world, port, log_n, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=120) for _ in range(world))
+    got = dict(q.get(timeout=180) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    P = pyref
+    plan = zdist.FourStepPlan(log_n, world)
     n = 1 << log_n
-    full = [P.splitmix64(1000 + i) * P.splitmix64(7 + i) % P.R_MOD for i in range(n)]
-    w = P.omega(log_n)
-    want = P.intt(full, w) if inverse else P.ntt(full, w)
-    raw = b"".join(got[r] for r in range(world))
-    assert [int.from_bytes(raw[32 * i:32 * i + 32], "little") for i in range(n)] == want
+    x = [pyref.splitmix64(17 * i + 3) % pyref.R_MOD for i in range(n)]
+    assert plan.natural_from_blocks_out([got[r] for r in range(world)]) == pyref.ntt(x, pyref.omega(log_n))
 
 
-def test_sharded_ntt_single_rank_matches(pyref):
-    """world = 1 runs the same four-step path without a process group."""
-    import torch
+def test_four_step_plan_shapes(zk):
     zdist = importlib.import_module("plutus-halo2-verifier-gen_b200.dist")
-    P = pyref
-    log_n = 6
-    n = 1 << log_n
-    full = [P.splitmix64(5 + i) % P.R_MOD for i in range(n)]
-    t = torch.frombuffer(bytearray(b"".join(v.to_bytes(32, "little") for v in full)), dtype=torch.uint8)
-    out = zdist.ShardedNTT(log_n, P.omega(log_n), 0, 1, ops=_CpuNttOps(P)).run(t)
-    raw = bytes(out.numpy())
-    assert [int.from_bytes(raw[32 * i:32 * i + 32], "little") for i in range(n)] == P.ntt(full, P.omega(log_n))
+    p = zdist.FourStepPlan(24, 8)
+    assert (p.log_r, p.log_c, p.Cl, p.Rl) == (11, 13, 1024, 256)
+    p = zdist.FourStepPlan(13, 8)
+    assert (p.log_r, p.log_c, p.Cl, p.Rl) == (10, 3, 1, 128)
+    with pytest.raises(ValueError):
+        zdist.FourStepPlan(3, 8)
+    with pytest.raises(ValueError):
+        zdist.FourStepPlan(20, 3)

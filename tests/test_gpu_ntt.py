@@ -136,28 +136,6 @@ def test_argument_errors(gpu):
     assert L.b200zk_ntt_fr(0, 1, gpu.capi.addr(one), 0, 0) == -1
 
 
-@pytest.mark.parametrize("log_n", [10, 16, 20])
-def test_four_step_plan_single_rank_matches_library(gpu, oracle, pyref, log_n):
-    """dist.ShardedNTT with world = 1 runs the multi-GPU decomposition (transposes, two batched transforms, the
-    omega^(i2 k1) block from b200zk_fr_power_table_dev) on one GPU: must equal the plain transform and the oracle."""
-    import importlib
-    import torch
-    zdist = importlib.import_module("plutus-halo2-verifier-gen_b200.dist")
-    n = 1 << log_n
-    data = oracle.synth_scalars(40 + log_n, 0, n)
-    w = pyref.omega(log_n)
-    t = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
-    out = zdist.ShardedNTT(log_n, w, 0, 1).run(t)
-    torch.cuda.synchronize()
-    got = bytes(out.cpu().numpy())
-    assert got == gpu_ntt(gpu, data, log_n, w)
-    if log_n <= 16:
-        assert got == oracle.ntt(data, log_n, fr(w))
-    inv = zdist.ShardedNTT(log_n, pyref.fr_inv(w), 0, 1, inverse=True).run(out)
-    torch.cuda.synchronize()
-    assert bytes(inv.cpu().numpy()) == data
-
-
 def test_pipelined_host_batch(gpu, oracle, pyref):
     """Host-buffer batches of >= 32 MiB are pipelined group by group (upload of the next group and download of the previous
     one under the current group's kernels): 8 x 2^17 elements, every polynomial against the oracle, plus coset + inverse."""

@@ -95,40 +95,17 @@ def main():
                                   "points_per_s": n / ms * 1e3, "e2e_ms": e2e, "e2e_points_per_s": n / e2e * 1e3,
                                   "imad_frac_48k_per_gpu": (n * bench.LMAC_PER_POINT / (ms * 1e-3)) / world / 9.22e12}), flush=True)
         zk.capi.check(lib.b200zk_bases_release(h.value))
-    # ---- one NTT sharded over the ranks (four-step, three exchanges) and a batch of independent NTTs split by rank
+    # ---- a batch of independent NTTs split by rank (no collective).  ONE transform over several GPUs runs from a single
+    #      process inside the library now (b200zk_ntt_fr / b200zk_ntt_fr_sharded_dev; measured by bench.py's single_process leg)
     for log_n in [int(x) for x in args.ntt_sizes.split(",") if x]:
         n = 1 << log_n
-        s0, s1 = zdist.shard_range(n, rank, world)
         w = pow(zk.host.ROOT_OF_UNITY, 1 << (32 - log_n), bench.R_MOD)
         wb = w.to_bytes(32, "little")
-        full = torch.from_numpy(bench.synth_scalars_np(bench.NTT_SEED, 0, n).view(np.uint8).reshape(-1)).cuda()
-        mine = full[32 * s0:32 * s1].clone()
-        plan = zdist.ShardedNTT(log_n, w, rank, world)
-        out = plan.run(mine)
-        zk.capi.check(lib.b200zk_ntt_fr_dev(full.data_ptr(), 1, log_n, zk.capi.addr(wb), 0, 0, st))   # single-GPU transform of the whole vector
-        ok = bool(torch.equal(out, full[32 * s0:32 * s1]))
-        okf = mx(0.0 if ok else 1.0) == 0.0
-        for _ in range(2):
-            plan.run(mine)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.reps):
-            plan.run(mine)
-        e1.record()
-        barrier()
-        ms = mx(e0.elapsed_time(e1)) / args.reps
-        e0.record()
-        for _ in range(args.reps):
-            zk.capi.check(lib.b200zk_ntt_fr_dev(full.data_ptr(), 1, log_n, zk.capi.addr(wb), 0, 0, st))
-        e1.record()
-        barrier()
-        ms1 = mx(e0.elapsed_time(e1)) / args.reps
-        # batch of 4 * world independent transforms of this size, split round-robin: no collective
         items = zdist.split_batch(4 * world, rank, world)
         batch = torch.from_numpy(bench.synth_scalars_np(5 + rank, 0, n * len(items)).view(np.uint8).reshape(-1)).cuda()
         zk.capi.check(lib.b200zk_ntt_fr_dev(batch.data_ptr(), len(items), log_n, zk.capi.addr(wb), 0, 0, st))
         barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.reps):
             zk.capi.check(lib.b200zk_ntt_fr_dev(batch.data_ptr(), len(items), log_n, zk.capi.addr(wb), 0, 0, st))
@@ -136,11 +113,9 @@ def main():
         barrier()
         msb = mx(e0.elapsed_time(e1)) / args.reps
         if rank == 0:
-            print(json.dumps({"op": "ntt_fr_sharded", "n_gpus": world, "log_n": log_n, "ms": ms, "elements_per_s": n / ms * 1e3,
-                              "single_gpu_ms": ms1, "speedup_vs_one_gpu": ms1 / ms, "matches_single_gpu_transform": okf,
-                              "exchanges": 3 if world > 1 else 0, "bytes_per_rank_per_exchange": 32 * n // world,
-                              "batch_split": {"transforms": 4 * world, "ms": msb, "elements_per_s": 4 * world * n / msb * 1e3}}), flush=True)
-        del full, mine, batch, plan
+            print(json.dumps({"op": "ntt_fr_batch_split", "n_gpus": world, "log_n": log_n, "transforms": 4 * world, "ms": msb,
+                              "elements_per_s": 4 * world * n / msb * 1e3}), flush=True)
+        del batch
         torch.cuda.empty_cache()
     if world > 1:
         dist.destroy_process_group()
