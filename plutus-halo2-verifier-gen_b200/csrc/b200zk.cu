@@ -778,9 +778,10 @@ int32_t msm_run(Ctx& c, Slot& sl, const BaseTable* tab, const uint32_t* d_bases,
         if (serial)
             LAUNCH(msm_reduce_kernel, (unsigned)((groups + 63) / 64), 64, 0, s, S_in, A_in, S_out, A_out, m, m_out,
                    (uint32_t)nwin, scale_log);
-        else if (groups <= 1184)
-            // top of the tree (up to one full wave of 256-thread CTAs): one CTA per group, 8 lanes per node, additions in 4
-            // product levels instead of 14 products
+        else if (groups <= 600)
+            // top of the tree: one CTA per group, 8 lanes per node, additions in 4 product levels instead of 14 products
+            // (only while the groups fit the machine at once: at 1 024 groups -- the second level of a 2^19-bucket tree -- this
+            // kernel takes 1.2 ms against 0.38 ms for one warp per group)
             LAUNCH(msm_reduce_coop8_kernel, (unsigned)groups, 256, 0, s, S_in, A_in, S_out, A_out, m, m_out, (uint32_t)nwin, scale_log);
         else
             LAUNCH(msm_reduce_coop_kernel, (unsigned)((groups + 3) / 4), 128, 0, s, S_in, A_in, S_out, A_out, m, m_out,

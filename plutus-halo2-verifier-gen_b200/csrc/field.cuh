@@ -227,19 +227,20 @@ template <class P> HD void mont_mp_rows(uint32_t* E, uint32_t* O) {
         // The product m * 0xffffffff = (m - c0) * 2^32 + (2^32 - m) with c0 = [m != 0]: the subtraction that forms m leaves
         // exactly that borrow behind, so `hi` is one subtract-with-borrow, no compare / select.  A borrow may only feed a
         // subtract and a carry only an add: PTX's flag after sub.cc is "not borrow" on the device (a + ~b + 1), so the two
-        // must not be mixed -- hence E[0] + m is formed by its own add, whose carry (again c0) enters the E row.
+        // must not be mixed -- hence E[0] + m is formed by its own add, whose carry (again c0) goes on into the O row.
         const uint32_t e0 = E[0];
         m = sub_cc(0, e0);
         const uint32_t hi = subc(m, 0);        // m - c0
-        E[0] = add_cc(e0, m);                  // = 0, carry c0
-        E[1] = addc_cc(E[1], 0);
-#pragma unroll
-        for (int j = 2; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], P::p(j), m, E[j], E[j + 1]);
-        O[N - 1] = addc(O[N - 1], 0);          // the carry that leaves E lands on O[N-1] (O is aligned one limb higher)
-        O[0] = add_cc(O[0], e0);               // 2^32 - m = E[0] (mod 2^32) because m = -E[0]
+        E[0] = add_cc(e0, m);                  // = 0, carry c0: a unit of limb 1 -- which is O[0]'s weight too (O is aligned one
+        O[0] = addc_cc(O[0], e0);              // limb higher), so it enters the O row directly; 2^32 - m = E[0] (mod 2^32)
         O[1] = addc_cc(O[1], hi);
 #pragma unroll
         for (int k = 2; k < N; k += 2) madc_wide_cc(O[k], O[k + 1], P::p(k + 1), m, O[k], O[k + 1]);
+        // E row: limbs 0 and 1 are done (E[0] = 0, E[1] unchanged); the carry that leaves E lands on O[N-1]
+        mad_wide_cc(E[2], E[3], P::p(2), m, E[2], E[3]);
+#pragma unroll
+        for (int j = 4; j < N; j += 2) madc_wide_cc(E[j], E[j + 1], P::p(j), m, E[j], E[j + 1]);
+        O[N - 1] = addc(O[N - 1], 0);
         return;
     }
     m = E[0] * P::M0;
