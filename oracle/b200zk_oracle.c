@@ -538,8 +538,9 @@ static u64 splitmix64(u64 x) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     return z ^ (z >> 31);
 }
-/* base i = a_i * G with a_i = splitmix64(seed + i) (64-bit discrete log, known to the tests) */
-void orc_g1_synth_bases(u64 seed, u64 start, u64 n, uint8_t *out, int nthreads) {
+/* base i = a_i * G with a_i = splitmix64(seed + i) (64-bit discrete log, known to the tests).
+ * Reference definition, double-and-add: kept for the cross-check of the windowed version below. */
+void orc_g1_synth_bases_naive(u64 seed, u64 start, u64 n, uint8_t *out, int nthreads) {
     orc_init();
     uint8_t gw[96]; orc_g1_generator(gw);
     g1a G; g1a_from_wire(&G, gw);
@@ -551,6 +552,63 @@ void orc_g1_synth_bases(u64 seed, u64 start, u64 n, uint8_t *out, int nthreads) 
         u64 k[FRN] = {splitmix64(seed + start + (u64)i), 0, 0, 0};
         g1j j; g1j_mul_bits(&j, &G, k, 64);
         g1j_to_wire(out + 96 * (u64)i, &j);
+    }
+}
+/* The same points, fast enough for 2^24 of them on the host (the CPU arm of bench.py synthesises its own bases): fixed-base
+ * windows (8 x 255 affine multiples of G, one mixed addition per non-zero byte of a_i) and one shared inversion per block of
+ * 256 points (Montgomery's trick) for the affine normalisation. */
+void orc_g1_synth_bases(u64 seed, u64 start, u64 n, uint8_t *out, int nthreads) {
+    orc_init();
+    uint8_t gw[96]; orc_g1_generator(gw);
+    g1a G; g1a_from_wire(&G, gw);
+    static g1a table[8][256];
+    static int table_done = 0;
+#pragma omp critical(orc_synth_table)
+    if (!table_done) {
+        g1j base; g1j_from_affine(&base, &G);
+        for (int w = 0; w < 8; w++) {
+            g1j acc; g1j_set_inf(&acc);
+            for (int d = 1; d < 256; d++) {
+                g1j_add(&acc, &acc, &base);
+                uint8_t wire[96]; g1j_to_wire(wire, &acc);
+                g1a_from_wire(&table[w][d], wire);
+            }
+            for (int k = 0; k < 8; k++) g1j_double(&base, &base);
+        }
+        table_done = 1;
+    }
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#endif
+    enum { BLK = 256 };
+    int64_t nblk = (int64_t)((n + BLK - 1) / BLK);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int64_t b = 0; b < nblk; b++) {
+        g1j pts[BLK]; fp pre[BLK];
+        u64 i0 = (u64)b * BLK, cnt = n - i0 < BLK ? n - i0 : BLK;
+        fp run; memcpy(run.l, FP_R, sizeof run.l);
+        for (u64 t = 0; t < cnt; t++) {
+            u64 k = splitmix64(seed + start + i0 + t);
+            g1j acc; g1j_set_inf(&acc);
+            for (int w = 0; w < 8; w++) {
+                unsigned d = (unsigned)(k >> (8 * w)) & 255u;
+                if (d) g1j_add_affine(&acc, &acc, &table[w][d], 0);
+            }
+            pts[t] = acc;
+            pre[t] = run;                               /* product of the z of the earlier points of the block */
+            if (!g1j_is_inf(&acc)) fp_mul(&run, &run, &acc.z);
+        }
+        fp inv; fp_inv(&inv, &run);
+        for (int64_t t = (int64_t)cnt - 1; t >= 0; t--) {
+            uint8_t *o = out + 96 * (i0 + (u64)t);
+            if (g1j_is_inf(&pts[t])) { memset(o, 0, 96); continue; }
+            fp zi, zi2, zi3, x, y;
+            fp_mul(&zi, &inv, &pre[t]);                 /* 1 / z_t */
+            fp_mul(&inv, &inv, &pts[t].z);
+            fp_sqr(&zi2, &zi); fp_mul(&zi3, &zi2, &zi);
+            fp_mul(&x, &pts[t].x, &zi2); fp_mul(&y, &pts[t].y, &zi3);
+            fp_to_bytes(o, &x); fp_to_bytes(o + 48, &y);
+        }
     }
 }
 /* scalar i: limbs w_j = splitmix64(seed + 4i + j), top limb masked to 63 bits (value < 2^255),

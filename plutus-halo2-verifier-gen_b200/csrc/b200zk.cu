@@ -125,6 +125,7 @@ struct TableSet {
 
 struct NttPlan {
     uint32_t log_n = 0, npass = 0;
+    uint32_t logb = NTT_LOGB;  // log2 of the CTA tile: 11, or 12 for the two-pass plans of 2^23 / 2^24
     uint32_t deg[3] = {0, 0, 0};
     uint32_t* tw_local[3] = {nullptr, nullptr, nullptr};
     uint32_t* tw_pass[3] = {nullptr, nullptr, nullptr};
@@ -888,7 +889,11 @@ int32_t ntt_get_plan(Ctx& c, uint32_t log_n, const uint8_t omega[32], bool inver
     cudaStream_t s = c.stream;
     NttPlan pl;
     pl.log_n = log_n;
-    pl.npass = (log_n + NTT_LOGB - 1) / NTT_LOGB;
+    // experiment (B200ZK_NTT_VARIANT=8): 2^23 and 2^24 as two passes over a 4096-element tile instead of three over a
+    // 2048-element one.  Measured at 2^24: 4.13 ms against 3.67 ms -- one 512-thread CTA per SM loses more at its barriers and
+    // load / store phases (0.18 ms per butterfly stage against 0.164) than the saved pass and twiddle product give back.
+    if (log_n > 2 * NTT_LOGB && log_n <= 2 * NTT_LOGB12 && g_ntt_variant == 8) pl.logb = NTT_LOGB12;
+    pl.npass = (log_n + pl.logb - 1) / pl.logb;
     if (pl.npass == 0) pl.npass = 1;
     if (pl.npass > 3) return fail(B200ZK_ERR_INVALID_ARG, "ntt: log_n > 33 is not supported");
     for (uint32_t i = 0; i < pl.npass; i++) pl.deg[i] = log_n / pl.npass + (i < log_n % pl.npass ? 1 : 0);
@@ -955,6 +960,7 @@ int32_t ntt_set_attrs(Ctx& c) {
     CU(cudaFuncSetAttribute(ntt_pass_kernel_wl2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
     CU(cudaFuncSetAttribute(ntt_pass_kernel_tw2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM_TW));
     CU(cudaFuncSetAttribute(ntt_pass_kernel_lb0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+    CU(cudaFuncSetAttribute(ntt_pass_kernel_lb0_t12, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM12));
     c.ntt_attr_set = true;
     return B200ZK_OK;
 }
@@ -1022,8 +1028,9 @@ int32_t ntt_run(Ctx& c, Slot& sl, uint32_t* d_data, uint32_t batch, uint32_t log
         a.log_s = log_s;
         a.log_cols = log_n - pl->deg[i];
         a.total_cols = (uint64_t)batch << a.log_cols;
-        uint64_t ctas = (total + NTT_B - 1) / NTT_B;
-        if (ntt_variant == 0) LAUNCH(ntt_pass_kernel, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+        uint64_t ctas = (total + ((uint64_t)1 << pl->logb) - 1) >> pl->logb;
+        if (pl->logb == NTT_LOGB12) LAUNCH(ntt_pass_kernel_lb0_t12, (unsigned)ctas, NTT_THREADS12, NTT_SMEM12, s, a);
+        else if (ntt_variant == 0) LAUNCH(ntt_pass_kernel, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         else if (ntt_variant == 2) LAUNCH(ntt_pass_kernel_call2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         else if (ntt_variant == 3) LAUNCH(ntt_pass_kernel_call3, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         else if (ntt_variant == 4) LAUNCH(ntt_pass_kernel_plain2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);

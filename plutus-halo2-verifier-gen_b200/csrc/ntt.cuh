@@ -59,17 +59,17 @@ template <bool WL> __device__ __forceinline__ uint32_t ntt_pos(uint32_t e) {
     if (WL) return e ^ ((((e >> 5) ^ (e >> 8)) & 7u) << 2) ^ ((e >> 6) & 3u);
     return e + (e >> 5);
 }
-template <bool WL> __device__ __forceinline__ Fr ntt_lds(const uint32_t* sm, uint32_t e) {
+template <bool WL, int PLANE = NTT_PLANE> __device__ __forceinline__ Fr ntt_lds(const uint32_t* sm, uint32_t e) {
     Fr r;
     uint32_t pos = ntt_pos<WL>(e);
 #pragma unroll
-    for (int w = 0; w < 8; w++) r.l[w] = sm[w * NTT_PLANE + pos];
+    for (int w = 0; w < 8; w++) r.l[w] = sm[w * PLANE + pos];
     return r;
 }
-template <bool WL> __device__ __forceinline__ void ntt_sts(uint32_t* sm, uint32_t e, const Fr& v) {
+template <bool WL, int PLANE = NTT_PLANE> __device__ __forceinline__ void ntt_sts(uint32_t* sm, uint32_t e, const Fr& v) {
     uint32_t pos = ntt_pos<WL>(e);
 #pragma unroll
-    for (int w = 0; w < 8; w++) sm[w * NTT_PLANE + pos] = v.l[w];
+    for (int w = 0; w < 8; w++) sm[w * PLANE + pos] = v.l[w];
 }
 __device__ __forceinline__ Fr ntt_ldg(const uint32_t* p) {
     const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -135,9 +135,10 @@ struct FrMulCall {
 // TWSM: the R/2 local twiddles were staged in shared memory (word planes like the data) by the caller, so a butterfly never
 // waits on a global load.  LB0: this is the sweep over index bits 0..NB-1, where the twiddle exponent of a butterfly depends
 // only on its position inside the thread (known at compile time): the multiplications by omega^0 disappear.
-template <int NB, class M, bool WL, bool TWSM = false, bool LB0 = false>
+template <int NB, class M, bool WL, bool TWSM = false, bool LB0 = false, int LOGB = NTT_LOGB>
 __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restrict__ tw_local, uint32_t deg,
                                           uint32_t lb, uint32_t tid) {
+    constexpr int PLANE = (1 << LOGB) + (1 << LOGB) / 32;
     if (LB0) lb = 0;
     uint32_t base;
     if (WL && lb + 2 <= 7) {
@@ -153,14 +154,14 @@ __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restri
             lo = tid & ((1u << lb) - 1);
             hi = tid >> lb;
         } else {
-            hi = tid & ((1u << (NTT_LOGB - 3 - lb)) - 1);
-            lo = tid >> (NTT_LOGB - 3 - lb);
+            hi = tid & ((1u << (LOGB - 3 - lb)) - 1);
+            lo = tid >> (LOGB - 3 - lb);
         }
         base = (hi << (lb + 3)) | lo;
     }
     Fr v[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) v[j] = ntt_lds<WL>(sm, base | ((uint32_t)j << lb));
+    for (int j = 0; j < 8; j++) v[j] = ntt_lds<WL, PLANE>(sm, base | ((uint32_t)j << lb));
     uint32_t rmask = (1u << deg) - 1;
 #pragma unroll
     for (int q = NB - 1; q >= 0; q--) {
@@ -177,25 +178,26 @@ __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restri
                 uint32_t il = (base | ((uint32_t)j << lb)) & rmask;
                 uint32_t e = (il & ((1u << b) - 1)) << (deg - 1 - b);
                 if (LB0) e = (uint32_t)(j & ((1 << q) - 1)) << (deg - 1 - b);
-                Fr w = TWSM ? ntt_lds<false>(sm + 8 * NTT_PLANE, e) : ntt_ldg(tw_local + 8 * (size_t)e);
+                Fr w = TWSM ? ntt_lds<false, PLANE>(sm + 8 * PLANE, e) : ntt_ldg(tw_local + 8 * (size_t)e);
                 v[j | (1 << q)] = M::mul(d, w);
             }
         }
     }
 #pragma unroll
-    for (int j = 0; j < 8; j++) ntt_sts<WL>(sm, base | ((uint32_t)j << lb), v[j]);
+    for (int j = 0; j < 8; j++) ntt_sts<WL, PLANE>(sm, base | ((uint32_t)j << lb), v[j]);
 }
 
-template <class M, bool WL, bool TWSM = false, bool LB0EN = TWSM>
+template <class M, bool WL, bool TWSM = false, bool LB0EN = TWSM, int LOGB = NTT_LOGB>
 __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     extern __shared__ uint32_t sm[];
+    constexpr int PLANE = (1 << LOGB) + (1 << LOGB) / 32, THREADS = (1 << LOGB) / 8;
     const uint32_t tid = threadIdx.x;
     const uint32_t deg = a.deg;
     if (TWSM && deg) {
         // the R/2 local twiddles into planes 8..15 (visible after the barrier that follows the data load)
-        for (uint32_t e = tid; e < (1u << (deg - 1)); e += NTT_THREADS) ntt_sts<false>(sm + 8 * NTT_PLANE, e, ntt_ldg(a.tw_local + 8 * (size_t)e));
+        for (uint32_t e = tid; e < (1u << (deg - 1)); e += THREADS) ntt_sts<false, PLANE>(sm + 8 * PLANE, e, ntt_ldg(a.tw_local + 8 * (size_t)e));
     }
-    const uint32_t logU = NTT_LOGB - deg;          // sub-transforms per CTA (log2)
+    const uint32_t logU = LOGB - deg;          // sub-transforms per CTA (log2)
     const uint64_t col0 = (uint64_t)blockIdx.x << logU;
     const uint64_t cmask = ((uint64_t)1 << a.log_cols) - 1;
 
@@ -205,7 +207,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     if (!a.in_scale) {
 #pragma unroll
         for (int t = 0; t < 8; t++) {
-            uint32_t idx = tid + t * NTT_THREADS;
+            uint32_t idx = tid + t * THREADS;
             uint32_t ul = idx & ((1u << logU) - 1), j = idx >> logU;
             uint64_t col = col0 + ul;
             Fr v = fe_zero<FrParams>();
@@ -214,12 +216,12 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
                 v = ntt_ld_stream(a.in + 8 * ((poly << a.log_n) + u + ((uint64_t)j << a.log_cols)));
                 if (a.reduce_in) fe_reduce_loose(v);
             }
-            ntt_sts<WL>(sm, (ul << deg) | j, v);
+            ntt_sts<WL, PLANE>(sm, (ul << deg) | j, v);
         }
     } else
 #pragma unroll 1
     for (int t = 0; t < 8; t++) {
-        uint32_t idx = tid + t * NTT_THREADS;
+        uint32_t idx = tid + t * THREADS;
         uint32_t ul = idx & ((1u << logU) - 1), j = idx >> logU;
         uint64_t col = col0 + ul;
         Fr v = fe_zero<FrParams>();
@@ -230,7 +232,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
             if (a.reduce_in) fe_reduce_loose(v);
             if (a.in_scale) v = M::mul(v, ntt_ld_stream(a.in_scale + 8 * (u + ((uint64_t)j << a.log_cols))));
         }
-        ntt_sts<WL>(sm, (ul << deg) | j, v);
+        ntt_sts<WL, PLANE>(sm, (ul << deg) | j, v);
     }
     __syncthreads();
 
@@ -240,12 +242,12 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
         int nb = rem >= 3 ? 3 : rem;
         uint32_t lb = (uint32_t)(rem - nb);
         if (LB0EN && lb == 0) {
-            if (nb == 3) ntt_group<3, M, WL, TWSM, true>(sm, a.tw_local, deg, 0, tid);
-            else if (nb == 2) ntt_group<2, M, WL, TWSM, true>(sm, a.tw_local, deg, 0, tid);
-            else ntt_group<1, M, WL, TWSM, true>(sm, a.tw_local, deg, 0, tid);
-        } else if (nb == 3) ntt_group<3, M, WL, TWSM>(sm, a.tw_local, deg, lb, tid);
-        else if (nb == 2) ntt_group<2, M, WL, TWSM>(sm, a.tw_local, deg, lb, tid);
-        else ntt_group<1, M, WL, TWSM>(sm, a.tw_local, deg, lb, tid);
+            if (nb == 3) ntt_group<3, M, WL, TWSM, true, LOGB>(sm, a.tw_local, deg, 0, tid);
+            else if (nb == 2) ntt_group<2, M, WL, TWSM, true, LOGB>(sm, a.tw_local, deg, 0, tid);
+            else ntt_group<1, M, WL, TWSM, true, LOGB>(sm, a.tw_local, deg, 0, tid);
+        } else if (nb == 3) ntt_group<3, M, WL, TWSM, false, LOGB>(sm, a.tw_local, deg, lb, tid);
+        else if (nb == 2) ntt_group<2, M, WL, TWSM, false, LOGB>(sm, a.tw_local, deg, lb, tid);
+        else ntt_group<1, M, WL, TWSM, false, LOGB>(sm, a.tw_local, deg, lb, tid);
         rem -= nb;
         // the next sweep works on bits below lb: if both this sweep and the next stay inside a warp's 256-element block
         // the warp only has to wait for itself
@@ -258,7 +260,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     const bool k_fast = (a.log_s == 0);
 #pragma unroll 1
     for (int t = 0; t < 8; t++) {
-        uint32_t idx = tid + t * NTT_THREADS;
+        uint32_t idx = tid + t * THREADS;
         uint32_t ul, k;
         if (k_fast) { k = idx & ((1u << deg) - 1); ul = idx >> deg; }
         else { ul = idx & ((1u << logU) - 1); k = idx >> logU; }
@@ -266,7 +268,7 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
         if (col >= a.total_cols) continue;
         uint32_t kr = __brev(k) >> (32 - deg);
         if (deg == 0) kr = 0;
-        Fr v = ntt_lds<WL>(sm, (ul << deg) | kr);
+        Fr v = ntt_lds<WL, PLANE>(sm, (ul << deg) | kr);
         uint64_t poly = col >> a.log_cols, u = col & cmask;
         uint64_t q = u & (((uint64_t)1 << a.log_s) - 1), p = u >> a.log_s;
         if (a.tw_pass) v = M::mul(v, ntt_ld_stream(a.tw_pass + 8 * ((p << deg) + k)));
@@ -292,6 +294,12 @@ constexpr size_t NTT_SMEM_TW = (size_t)16 * NTT_PLANE * sizeof(uint32_t);
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_tw2(NttPassArgs a) { ntt_pass_body<FrMulInline, false, true>(a); }
 // compile-time exponents in the lowest sweep only (twiddles stay in global memory / L1)
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_lb0(NttPassArgs a) { ntt_pass_body<FrMulInline, false, false, true>(a); }
+// the same with a 4096-element tile (132 KiB of shared memory, 512 threads, one CTA per SM -- the same 16 warps per SM): a
+// transform of 2^23 / 2^24 points then takes two passes of radix <= 2^12 instead of three of radix 2^8
+constexpr int NTT_LOGB12 = 12;
+constexpr int NTT_THREADS12 = (1 << NTT_LOGB12) / 8;
+constexpr size_t NTT_SMEM12 = (size_t)8 * ((1 << NTT_LOGB12) + (1 << NTT_LOGB12) / 32) * sizeof(uint32_t);
+__global__ void __launch_bounds__(NTT_THREADS12, 1) ntt_pass_kernel_lb0_t12(NttPassArgs a) { ntt_pass_body<FrMulInline, false, false, true, NTT_LOGB12>(a); }
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_call2(NttPassArgs a) { ntt_pass_body<FrMulCall, false>(a); }
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_plain2(NttPassArgs a) { ntt_pass_body<FrMulPlain, false>(a); }
 __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel_call3(NttPassArgs a) { ntt_pass_body<FrMulCall, false>(a); }

@@ -86,8 +86,26 @@ def test_2pow22_full_parity(gpu, oracle, pyref):
     assert gpu_ntt(gpu, fwd, log_n, pyref.fr_inv(w), gpu.NTT_INVERSE_SCALE) == data
 
 
+@pytest.mark.parametrize("log_n", [23, 24])
+def test_2pow23_2pow24_full_parity(gpu, oracle, pyref, log_n):
+    """The three-pass sizes: forward, coset and inverse, byte-identical to the oracle in full."""
+    n = 1 << log_n
+    data = oracle.synth_scalars(40 + log_n, 0, n)
+    w = pyref.omega(log_n)
+    fwd = gpu_ntt(gpu, data, log_n, w)
+    assert fwd == oracle.ntt(data, log_n, fr(w))
+    assert gpu_ntt(gpu, fwd, log_n, pyref.fr_inv(w), gpu.NTT_INVERSE_SCALE) == data
+    if log_n == 23:
+        cos = gpu_ntt(gpu, data, log_n, w, gpu.NTT_COSET_IN, 7)
+        assert cos == oracle.ntt(data, log_n, fr(w), 0, fr(7))
+        assert gpu_ntt(gpu, cos, log_n, pyref.fr_inv(w), gpu.NTT_INVERSE_SCALE | gpu.NTT_COSET_OUT, pyref.fr_inv(7)) == data
+        # a batch of two, Montgomery data
+        two = data[:32 * (n // 2)] * 2   # two polynomials of 2^22 each
+        assert gpu_ntt(gpu, two, log_n - 1, pyref.omega(log_n - 1), 0, None, 2) == oracle.ntt(two[:32 * (n // 2)], log_n - 1, fr(pyref.omega(log_n - 1))) * 2
+
+
 def test_2pow24_properties(gpu, oracle, pyref):
-    """Largest bench size (three passes): inverse(forward(x)) == x and one output checked by Horner."""
+    """Largest bench size: inverse(forward(x)) == x and two outputs checked against sums of the input."""
     log_n = 24
     n = 1 << log_n
     data = oracle.synth_scalars(3, 0, n)

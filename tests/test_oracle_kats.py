@@ -191,3 +191,16 @@ def test_c_oracle_ntt_cross_checks(oracle, pyref):
         cos = b"".join(pyref.fr_to_le(x) for x in pyref.coset_ntt(a, w, 7))
         assert oracle.ntt(data, k, pyref.fr_to_le(w), 0, pyref.fr_to_le(7)) == cos
         assert oracle.ntt(cos, k, pyref.fr_to_le(pyref.fr_inv(w)), 1, None, pyref.fr_to_le(pyref.fr_inv(7))) == data
+
+
+def test_c_oracle_synthetic_bases_windowed_equals_double_and_add(oracle, pyref):
+    """The fast base generator of the CPU arm (fixed-base windows + one inversion per block of 256) against the plain
+    double-and-add definition, across block boundaries and for a start offset, and against the big-integer definition."""
+    import ctypes as C
+    L = oracle.L
+    L.orc_g1_synth_bases_naive.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_char_p, C.c_int]
+    for start, n in ((0, 1), (0, 255), (0, 256), (5, 257), (1000, 1200)):
+        a = C.create_string_buffer(96 * n)
+        L.orc_g1_synth_bases_naive(0xB200, start, n, a, 0)
+        assert oracle.synth_bases(0xB200, start, n) == a.raw, (start, n)
+    assert pyref.g1_from_wire(oracle.synth_bases(0xB200, 3, 1)) == pyref.g1_mul(pyref.G1_GEN, pyref.synth_base_dlog(0xB200, 3))
