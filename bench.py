@@ -427,6 +427,14 @@ def main():
                             "host-buffer route and resident route; CPU column = the checker's port, sampled calls scaled by the call counts",
                     "traces": [circuit_bench.run_circuit(zk, lib, L, name, 3, True, host_threads()) for name in ("atms17", "atms19")]}
 
+    # ---------------------------------------------------------------- batched verification up to the pairing (BASELINE configs[4])
+    verify = None
+    if rank == 0 and world == 1 and not args.no_circuits:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import verify_bench
+        verify = verify_bench.run_batched_verify(zk, None if args.no_cpu else load_oracle())
+        assert verify["accepted_s_left_eq_right"] in (True, None), "the batched guards do not verify"
+
     # ---------------------------------------------------------------- N > 1: ONE process driving all N GPUs through the plain C ABI
     single = None
     if world > 1 and not args.no_single_process:
@@ -480,6 +488,7 @@ def main():
             "cpu_baseline": cpu,
             "ntt": ntt,
             "circuits": circuits,
+            "batched_verify": verify,
             "single_process": single,
             "result_compressed": zk.host.g1_compress(result_dev).hex(),
         }
@@ -544,7 +553,11 @@ def bench_single_process(zk, lib, torch, np, args, n_gpus, expect):
         rec = circuit_bench.run_circuit(zk, lib, None, "atms19", 3, False, 0)
         proof = {k: rec[k] for k in ("circuit", "k", "commitments", "ntt_columns", "gpu_trace_ms", "gpu_msm_ms", "gpu_ntt_ms")}
         proof["note"] = "host buffers in and out, host clock; compare with circuits.traces[atms19].gpu_trace_ms of the 1-GPU line"
-    return {"n_gpus": n_gpus, "ntt_sharded": ntt, "proof_columns_over_gpus": proof, "e2e_single_process": {"value": n / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
+    verify = None
+    if not args.no_circuits:
+        import verify_bench
+        verify = verify_bench.run_batched_verify(zk, None if args.no_cpu else load_oracle())
+    return {"n_gpus": n_gpus, "ntt_sharded": ntt, "proof_columns_over_gpus": proof, "batched_verify": verify, "e2e_single_process": {"value": n / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
                                                      "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 96},
             "resident_single_process": {"value": n / (res_ms * 1e-3), "unit": "points/s", "ms_per_step": res_ms},
             "table_build_ms": build_ms, "parity_with_per_rank_path": True,
