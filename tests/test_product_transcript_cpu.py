@@ -104,3 +104,56 @@ def test_h2mo_argument_errors(zk):
     assert rc == -4
     out = C.create_string_buffer(96)
     assert zk.lib().b200zk_guard_eval(None, 0, None, zk.capi.addr(out), zk.capi.addr(out)) == -1
+
+
+def test_h2mo_scalars_random_structures_vs_restatement(zk, pyref):
+    """The library's host field arithmetic (64-bit-limb Montgomery products in csrc/h2mo.cu) against Python integers on random
+    query structures whose points, evaluations and challenges include the edges of the field (0, 1, r - 1, 2^k neighbours)."""
+    import random
+    R = pyref.R_MOD
+    rnd = random.Random(2024)
+    edge = [0, 1, 2, R - 1, R - 2, (1 << 64) - 1, 1 << 64, (1 << 128) - 1, 1 << 192, (1 << 254) % R, R >> 1, (R >> 1) + 1]
+    fr = zk.host.fr_bytes
+
+    def pick():
+        return rnd.choice(edge) if rnd.random() < 0.3 else rnd.randrange(R)
+
+    for trial in range(40):
+        n_comm = rnd.randrange(1, 9)
+        n_pts = rnd.randrange(1, 5)
+        pts_pool = []
+        while len(pts_pool) < n_pts:                      # distinct points; x3 must differ from all of them
+            p = pick()
+            if p not in pts_pool:
+                pts_pool.append(p)
+        queries = []
+        for ci in range(n_comm):
+            for p in rnd.sample(pts_pool, rnd.randrange(1, n_pts + 1)):
+                queries.append((ci, p, pick()))
+        rnd.shuffle(queries)
+        x1, x2, x4 = pick(), pick(), pick()
+        x3 = pick()
+        while x3 in pts_pool:
+            x3 = rnd.randrange(R)
+        psets, members, ev = pyref.h2mo_sets(queries)
+        pq = [pick() for _ in psets]
+        cmap = [(None, si, psets[si], ev[p]) for si, mem in enumerate(members) for p in mem]
+        want_qes = pyref.h2mo_q_eval_sets(cmap, len(psets), x1)
+        want_f = pyref.h2mo_f_eval(psets, want_qes, x2, x3, pq)
+        want_v = pyref.h2mo_v(want_f, x4, pq)
+        qc = (C.c_uint32 * len(queries))(*[q[0] for q in queries])
+        pts = b"".join(fr(q[1]) for q in queries)
+        evs = b"".join(fr(q[2]) for q in queries)
+        ch = b"".join(fr(x) for x in (x1, x2, x3, x4))
+        pqb = b"".join(fr(x) for x in pq)
+        total = sum(len(ps) for ps in psets)
+        qes = C.create_string_buffer(32 * total)
+        f_eval, v = C.create_string_buffer(32), C.create_string_buffer(32)
+        zk.capi.check(zk.lib().b200zk_h2mo_scalars(n_comm, C.addressof(qc), zk.capi.addr(pts), zk.capi.addr(evs), len(queries),
+                                                   zk.capi.addr(ch), zk.capi.addr(pqb), len(psets), zk.capi.addr(qes), len(qes),
+                                                   zk.capi.addr(f_eval), zk.capi.addr(v)))
+        got = [int.from_bytes(qes.raw[32 * i:32 * i + 32], "little") for i in range(total)]
+        flat = [want_qes[si][j] for si, ps in enumerate(psets) for j in range(len(ps))]
+        assert got == flat, trial
+        assert int.from_bytes(f_eval.raw, "little") == want_f, trial
+        assert int.from_bytes(v.raw, "little") == want_v, trial
