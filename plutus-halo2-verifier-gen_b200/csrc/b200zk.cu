@@ -1825,7 +1825,11 @@ cudaStream_t stream(Dev* d) { return d->stream; }
 int sm_count(Dev* d) { return d->prop.multiProcessorCount; }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int32_t generator_dev(Dev* d, uint32_t** out, cudaStream_t s) { return get_generator_dev(*d, out, s); }
-void on_shutdown(void (*fn)()) { g_hooks.push_back(fn); }
+void on_shutdown(void (*fn)()) {
+    static std::mutex mu;   // the other translation units register from under their own locks
+    std::lock_guard<std::mutex> lk(mu);
+    g_hooks.push_back(fn);
+}
 int32_t ws_enter(Dev* d, cudaStream_t s) {
     if (!d->ws_event) XCU(cudaEventCreateWithFlags(&d->ws_event, cudaEventDisableTiming));
     if (d->ws_used && s != d->ws_stream) XCU(cudaStreamWaitEvent(s, d->ws_event, 0));

@@ -19,6 +19,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -357,14 +360,68 @@ int32_t eval_terms(const std::vector<Term>& terms, uint8_t out[96]) {
     return b200zk_msm_g1_adhoc(aff.data(), B200ZK_FMT_CANONICAL, sc.data(), B200ZK_FMT_CANONICAL, n, out);
 }
 
-struct DevMem {   // device scratch of one multi_open, freed on every exit path
-    std::vector<void*> ptrs;
-    int32_t alloc(void** out, size_t bytes) {
-        XTRY(b200zk_dev_alloc(out, bytes));
-        ptrs.push_back(*out);
+// Device scratch of one multi_open: a grow-only arena per concurrent call and device, kept between calls.  cudaMalloc / cudaFree
+// inside the flow were measured at tens to hundreds of milliseconds per opening (and one ~0.9 s stall in five calls at k = 19)
+// against 8-40 ms for everything else, so the flow allocates nothing once it has run at its largest size.
+struct Arena {
+    int ordinal = -1;
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    bool busy = false;
+};
+std::mutex g_arena_mu;
+std::vector<Arena*>* g_arenas = nullptr;   // leaked on purpose (no static destruction order games); emptied by b200zk_shutdown
+void arenas_shutdown() {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    if (!g_arenas) return;
+    for (Arena* a : *g_arenas) {
+        if (a->p) {
+            ctx::DeviceScope scope(a->ordinal);
+            cudaFree(a->p);
+        }
+        delete a;
+    }
+    g_arenas->clear();
+}
+struct DevMem {
+    Arena* a = nullptr;
+    size_t used = 0;
+    // the caller has made `ordinal` the current CUDA device
+    int32_t reserve(int ordinal, size_t bytes) {
+        {
+            std::lock_guard<std::mutex> lk(g_arena_mu);
+            if (!g_arenas) {
+                g_arenas = new std::vector<Arena*>();
+                ctx::on_shutdown(arenas_shutdown);
+            }
+            for (Arena* c : *g_arenas)   // a free arena of this device, the largest first choice
+                if (!c->busy && c->ordinal == ordinal && (!a || c->cap > a->cap)) a = c;
+            if (!a) {
+                a = new Arena();
+                a->ordinal = ordinal;
+                g_arenas->push_back(a);
+            }
+            a->busy = true;
+        }
+        if (a->cap < bytes) {
+            if (a->p) XCU(cudaFree(a->p));
+            a->p = nullptr;
+            a->cap = 0;
+            XCU(cudaMalloc(&a->p, bytes));
+            a->cap = bytes;
+        }
         return B200ZK_OK;
     }
-    ~DevMem() { for (void* p : ptrs) b200zk_dev_free(p); }
+    void* take(size_t bytes) {
+        void* r = a->p + used;
+        used += (bytes + 255) & ~(size_t)255;
+        return r;
+    }
+    ~DevMem() {
+        if (!a) return;
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        a->busy = false;
+    }
 };
 
 }  // namespace
@@ -414,6 +471,16 @@ int32_t b200zk_h2mo_open_dev(uint64_t bases, uint64_t transcript, const void* co
     if (!tr) return ctx::fail(B200ZK_ERR_BAD_HANDLE, "unknown transcript handle");
     if (!d_polys || !query_poly || !query_points || !out_proof || !out_len || n_polys == 0 || n_queries == 0 || n == 0)
         return ctx::fail(B200ZK_ERR_INVALID_ARG, "multi-open: null pointer or empty query list");
+    // B200ZK_H2MO_TIMING=1: phase times on stderr (the device is synchronised at every mark; diagnostics only)
+    static const bool timing = getenv("B200ZK_H2MO_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!timing) return;
+        cudaDeviceSynchronize();
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[h2mo_open n=%llu] %-14s %8.3f ms\n", (unsigned long long)n, what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
     Sets sets;
     XTRY(build_sets(n_polys, query_poly, query_points, nullptr, n_queries, sets));
     const size_t S = sets.points.size();
@@ -422,18 +489,20 @@ int32_t b200zk_h2mo_open_dev(uint64_t bases, uint64_t transcript, const void* co
     if (cap < need) return ctx::fail(B200ZK_ERR_INVALID_ARG, "multi-open: proof buffer too small");
     for (auto& pts : sets.points)
         if (pts.size() >= n) return ctx::fail(B200ZK_ERR_INVALID_ARG, "multi-open: more opening points than coefficients");
+    ctx::Dev* dev = nullptr;
+    XTRY(ctx::for_pointer(d_polys[0], &dev));
+    ctx::DeviceScope scope(ctx::ordinal(dev));
     DevMem mem;
-    const size_t pb = (size_t)n * 32;
+    const size_t pb = ((size_t)n * 32 + 255) & ~(size_t)255;
+    size_t M = S;                                      // slots of the small staging area: evaluations | interpolation coefficients
+    for (auto& pts : sets.points) M = std::max(M, pts.size());
+    XTRY(mem.reserve(ctx::ordinal(dev), (S + 3) * pb + 64 * M + 96 + 512));
     std::vector<void*> Q(S);
-    void *G = nullptr, *T = nullptr, *F = nullptr, *small = nullptr, *d_pt = nullptr;
-    for (size_t s = 0; s < S; s++) XTRY(mem.alloc(&Q[s], pb));
-    XTRY(mem.alloc(&G, pb));
-    XTRY(mem.alloc(&T, pb));
-    XTRY(mem.alloc(&F, pb));
-    XTRY(mem.alloc(&small, 32 * 64));
-    XTRY(mem.alloc(&d_pt, 96));
+    for (size_t s = 0; s < S; s++) Q[s] = mem.take(pb);
+    void *G = mem.take(pb), *T = mem.take(pb), *F = mem.take(pb), *small = mem.take(64 * M), *d_pt = mem.take(96);
     uint8_t tmp[32];
     auto canon = [&](const Fr& x, uint8_t out[32]) { fr_store(x, out); };
+    mark("sets+alloc");
 
     // x1: q_s = sum_j x1^j p_{s,j}
     Fr x1 = tr->squeeze();
@@ -450,6 +519,7 @@ int32_t b200zk_h2mo_open_dev(uint64_t bases, uint64_t transcript, const void* co
         }
         XTRY(b200zk_fr_lincomb_dev(ps.data(), cf.data(), (uint32_t)ps.size(), Q[s], n, nullptr));
     }
+    mark("q_s lincombs");
     // x2: f = sum_s x2^s (q_s - r_s) / Z_s, r_s the interpolation of q_s on its point set, Z_s = prod (X - point)
     Fr x2 = tr->squeeze();
     std::vector<Fr> x2p = powers(x2, S);
@@ -471,8 +541,8 @@ int32_t b200zk_h2mo_open_dev(uint64_t bases, uint64_t transcript, const void* co
         XCU(cudaMemcpyAsync(G, Q[s], pb, cudaMemcpyDeviceToDevice, nullptr));
         std::vector<uint8_t> rb(32 * m);
         for (size_t k = 0; k < m; k++) memcpy(&rb[32 * k], r[k].l, 32);
-        XTRY(b200zk_dev_upload((uint8_t*)small + 32 * 32, rb.data(), 32 * m));
-        XTRY(b200zk_fr_pointwise_dev(2, G, (uint8_t*)small + 32 * 32, nullptr, G, m, nullptr));
+        XTRY(b200zk_dev_upload((uint8_t*)small + 32 * M, rb.data(), 32 * m));
+        XTRY(b200zk_fr_pointwise_dev(2, G, (uint8_t*)small + 32 * M, nullptr, G, m, nullptr));
         uint64_t len = n;
         void *src = G, *dst = T;
         for (size_t k = 0; k < m; k++) {
@@ -486,10 +556,12 @@ int32_t b200zk_h2mo_open_dev(uint64_t bases, uint64_t transcript, const void* co
         XTRY(b200zk_fr_pointwise_dev(3, src, nullptr, tmp, dst, n, nullptr));
         XTRY(b200zk_fr_pointwise_dev(1, F, dst, nullptr, F, n, nullptr));
     }
+    mark("f polynomial");
     // f commitment
     uint8_t aff[96], comp[48];
     XTRY(b200zk_msm_g1_dev(bases, 0, F, n, 1, B200ZK_FMT_MONT, nullptr, d_pt, nullptr));
     XTRY(b200zk_dev_download(aff, d_pt, 96));
+    mark("commit f");
     XTRY(b200zk_g1_compress(aff, comp));
     tr->common_point(comp);
     memcpy(out_proof, comp, 48);
@@ -508,6 +580,7 @@ int32_t b200zk_h2mo_open_dev(uint64_t bases, uint64_t transcript, const void* co
             tr->common_scalar(out_proof + 48 + 32 * s);
         }
     }
+    mark("q_s(x3)");
     // x4: final = sum_s x4^s q_s + x4^S f; pi commits to (final - final(x3)) / (X - x3)
     Fr x4 = tr->squeeze();
     {
@@ -519,8 +592,10 @@ int32_t b200zk_h2mo_open_dev(uint64_t bases, uint64_t transcript, const void* co
         XTRY(b200zk_fr_lincomb_dev(ps.data(), cf.data(), (uint32_t)ps.size(), G, n, nullptr));
     }
     XTRY(b200zk_fr_kate_div_dev(G, n, x3b, T, nullptr, nullptr));
+    mark("final / (X-x3)");
     XTRY(b200zk_msm_g1_dev(bases, 0, T, n - 1, 1, B200ZK_FMT_MONT, nullptr, d_pt, nullptr));
     XTRY(b200zk_dev_download(aff, d_pt, 96));
+    mark("commit pi");
     XTRY(b200zk_g1_compress(aff, comp));
     tr->common_point(comp);
     memcpy(out_proof + 48 + 32 * S, comp, 48);

@@ -93,6 +93,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.reps
+            zk.capi.check(lib.b200zk_ntt_fr(h_d.data_ptr(), log_n, zk.capi.addr(om), flags, zk.capi.addr(shift)))   # staging buffers grow once
             t0 = time.perf_counter()
             for _ in range(args.reps):
                 zk.capi.check(lib.b200zk_ntt_fr(h_d.data_ptr(), log_n, zk.capi.addr(om), flags, zk.capi.addr(shift)))
@@ -100,7 +101,8 @@ def main():
             passes = 1 if log_n <= 11 else (2 if log_n <= 22 else 3)
             lmacs = (n // 2) * log_n * bench.LMAC_PER_FR_MUL
             print(json.dumps({"op": "ntt_fr", "log_n": log_n, "variant": label, "ms": ms, "elements_per_s": n / ms * 1e3, "e2e_ms": e2e,
-                              "hbm_gbs": passes * 64 * n / (ms * 1e-3) / 1e9, "imad_frac": (lmacs / (ms * 1e-3)) / imad_peak,
+                              "hbm_gbs": passes * 64 * n / (ms * 1e-3) / 1e9, "imad_frac_136_per_product": (lmacs / (ms * 1e-3)) / imad_peak,
+                              "imad_frac_issued": ((n // 2) * log_n * 113 / (ms * 1e-3)) / imad_peak,
                               "passes": passes}), flush=True)
 
 
