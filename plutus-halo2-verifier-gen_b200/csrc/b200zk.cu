@@ -299,6 +299,9 @@ Ctx* g_prof_ctx = nullptr;
 Slot* g_prof_slot = nullptr;
 int g_ntt_variant = 7;            // 7: two CTAs per SM, compile-time twiddle exponents in the lowest sweep (default); 1: without them;
                                   // 0: one CTA per SM; 2..6 experiments.  B200ZK_NTT_VARIANT overrides.
+int64_t g_coop8_max = 0;           // top of the bucket tree: CTA-per-group kernel while there are at most this many groups (0 = one per SM)
+int g_red_tp = 0;                  // bucket-tree levels with many groups: throughput build with this many CTAs of 128 threads per SM (0 = off)
+int64_t g_red_tp_min = 1ll << 16;  // ... from this many groups
 int64_t g_chunk_min = 1ll << 20;  // a single host-buffer MSM of at least this many points streams its scalars in two pieces
                                   // (measured end to end, pinned scalars: 2^21 12.38 -> 11.72 ms, 2^22 23.02 -> 21.33 ms; this is also what
                                   // each GPU of a sharded 2^24 MSM does with its 2^21..2^23-point slice)
@@ -311,6 +314,9 @@ uint64_t g_range_split_min = 1ull << 16;              // single MSMs with at lea
 void read_env() {
     if (const char* v = getenv("B200ZK_NTT_VARIANT")) g_ntt_variant = atoi(v);
     if (const char* v = getenv("B200ZK_MSM_CHUNK_MIN")) g_chunk_min = atoll(v);
+    if (const char* v = getenv("B200ZK_COOP8_MAX")) g_coop8_max = atoll(v);
+    if (const char* v = getenv("B200ZK_RED_TP")) g_red_tp = atoi(v);
+    if (const char* v = getenv("B200ZK_RED_TP_MIN")) g_red_tp_min = atoll(v);
     if (const char* v = getenv("B200ZK_BATCH_STREAM_MIN_BYTES")) { g_batch_stream_min = (size_t)atoll(v); if (!g_batch_stream_min) g_batch_stream_min = 1; }
     if (const char* v = getenv("B200ZK_NTT_PIPE_MIN_BYTES")) g_ntt_pipe_min = atoll(v);
     if (const char* v = getenv("B200ZK_SCATTER_PASSES")) g_scatter_passes_env = atoi(v);
@@ -569,6 +575,18 @@ uint32_t msm_choose_window(uint64_t n, uint32_t batch, bool shared) {
     return best_c;
 }
 
+// Window bits of a table's rows, fixed when it is registered.  The model above is calibrated on single MSMs; a prover-size
+// table (k <= 19) is mostly committed against in batches (18-43 columns per phase), where every column reduces its own
+// bucket set and the tail is bound by throughput, not latency.  Measured on B200 (tools/batch_phases.py,
+// profiles/README.md "window bits of prover-size tables"): k = 13, 14: c = 16 beats the model's 15 for single columns
+// (1.03 against 1.45 ms at k = 14) and ties for batches; k = 15..18: 16 either way; k = 19: 18 beats 19 for an 18-column
+// batch (19.3 against 21.9 ms) and is within 0.4 ms for a single column; k = 20: 20 (the model's) wins for single MSMs.
+uint32_t table_window_bits(uint64_t n) {
+    if (n > (1ull << 12) && n <= (1ull << 18)) return 16;
+    if (n > (1ull << 18) && n <= (1ull << 19)) return 18;
+    return std::max(msm_choose_window(n, 1, true), 8u);   // c >= 8: at most 32 rows
+}
+
 MsmPlan msm_plan(uint64_t n, uint32_t batch, const BaseTable* tab) {
     MsmPlan pl{};
     bool precomp = tab && tab->rows > 1 && n * 16 >= tab->n;   // tiny slices of a big table: plain path
@@ -776,13 +794,20 @@ int32_t msm_run(Ctx& c, Slot& sl, const BaseTable* tab, const uint32_t* d_bases,
         uint32_t* S_out = sl.redS[pp].as<uint32_t>();
         uint32_t* A_out = sl.redA[pp].as<uint32_t>();
         uint64_t groups = (uint64_t)m_out * nwin;
-        if (serial)
+        if (serial && g_red_tp > 0 && groups >= (uint64_t)g_red_tp_min) {
+            // enough groups to fill the machine: the throughput build of the same level (msm.cuh)
+            if (g_red_tp == 3)
+                LAUNCH(msm_reduce_tp_kernel<3>, (unsigned)((groups + 127) / 128), 128, 0, s, S_in, A_in, S_out, A_out, m, m_out, (uint32_t)nwin, scale_log);
+            else
+                LAUNCH(msm_reduce_tp_kernel<4>, (unsigned)((groups + 127) / 128), 128, 0, s, S_in, A_in, S_out, A_out, m, m_out, (uint32_t)nwin, scale_log);
+        } else if (serial)
             LAUNCH(msm_reduce_kernel, (unsigned)((groups + 63) / 64), 64, 0, s, S_in, A_in, S_out, A_out, m, m_out,
                    (uint32_t)nwin, scale_log);
-        else if (groups <= 600)
+        else if (groups <= (uint64_t)(g_coop8_max > 0 ? g_coop8_max : c.prop.multiProcessorCount))
             // top of the tree: one CTA per group, 8 lanes per node, additions in 4 product levels instead of 14 products
-            // (only while the groups fit the machine at once: at 1 024 groups -- the second level of a 2^19-bucket tree -- this
-            // kernel takes 1.2 ms against 0.38 ms for one warp per group)
+            // (only while the groups fit the machine at once -- the kernel holds one CTA per SM: at 1 024 groups this kernel takes
+            // 1.2 ms against 0.38 ms for one warp per group, and the 512-group level of a 2^18-bucket tree cost a single 2^19
+            // MSM 0.38 ms of its 1.75 ms tail while the limit stood at 600 groups)
             LAUNCH(msm_reduce_coop8_kernel, (unsigned)groups, 256, 0, s, S_in, A_in, S_out, A_out, m, m_out, (uint32_t)nwin, scale_log);
         else
             LAUNCH(msm_reduce_coop_kernel, (unsigned)((groups + 3) / 4), 128, 0, s, S_in, A_in, S_out, A_out, m, m_out,
@@ -1616,7 +1641,7 @@ int32_t register_shard(Ctx& c, TableShard& sh, const uint8_t* h_src, const uint8
     bool want_rows = !(fmt_flags & B200ZK_BASES_NO_WINDOW_TABLES) && !g_tune_no_tables && n >= 1024;
     uint32_t cbits = 0, W = 1;
     if (want_rows) {
-        cbits = (g_tune_c >= 2 && g_tune_c <= 24) ? g_tune_c : std::max(msm_choose_window(n, 1, true), 8u);   // c >= 8: at most 32 rows
+        cbits = (g_tune_c >= 2 && g_tune_c <= 24) ? g_tune_c : table_window_bits(n);
         W = (256 + cbits - 1) / cbits;
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);

@@ -163,6 +163,30 @@ __device__ __forceinline__ void xyzz_add_mixed_t(G1Xyzz& acc, const G1Affine& q,
     acc.y = M::mulsub(r, fe_sub(qq, x3), acc.y, ppp);
     acc.x = x3;
 }
+// acc += q, both XYZZ, for kernels that are bound by throughput rather than by the latency of one addition (the lowest levels
+// of the bucket tree): products out of line like the accumulate kernel's, ordered so that an input dies as early as possible
+template <class M>
+__device__ __forceinline__ void xyzz_add_tp(G1Xyzz& acc, const G1Xyzz& q) {
+    if (xyzz_is_inf(q)) return;
+    if (xyzz_is_inf(acc)) { acc = q; return; }
+    Fp u1 = M::mul(acc.x, q.zz);
+    Fp s1 = M::mul(acc.y, q.zzz);
+    Fp p = fe_sub(M::mul(q.x, acc.zz), u1);
+    Fp r = fe_sub(M::mul(q.y, acc.zzz), s1);
+    if (fe_is_zero(p)) {
+        if (fe_is_zero(r)) xyzz_dbl_t<M>(acc);             // same point
+        else xyzz_set_inf(acc);                              // opposite points
+        return;
+    }
+    Fp pp = M::sqr(p);
+    acc.zz = M::mul(M::mul(acc.zz, q.zz), pp);
+    Fp qq = M::mul(u1, pp);
+    Fp ppp = M::mul(p, pp);
+    acc.zzz = M::mul(M::mul(acc.zzz, q.zzz), ppp);
+    Fp x3 = fe_sub(fe_sub(fe_sub(M::sqr(r), ppp), qq), qq);
+    acc.y = M::mulsub(r, fe_sub(qq, x3), s1, ppp);
+    acc.x = x3;
+}
 __device__ __forceinline__ void xyzz_add_mixed_ni(G1Xyzz& acc, const G1Affine& q, bool neg) {
     xyzz_add_mixed_t<MulCall>(acc, q, neg);
 }

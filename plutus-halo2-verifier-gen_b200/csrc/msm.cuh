@@ -442,6 +442,43 @@ __global__ void __launch_bounds__(64) msm_reduce_kernel(const uint32_t* __restri
     xyzz_st(A_out, (uint64_t)w * m_out + g, asum);
 }
 
+// The same level for the case that there are enough groups to fill the machine several times over (a 2^24-point MSM reduces
+// 2^21 buckets; a prover's batch of 18 columns at k = 19 reduces 18 x 2^18): what counts then is throughput, and the kernel above
+// -- additions with inlined products for the latency of ONE addition, 255 registers, 8 warps per SM -- reaches less than half of
+// the multiplier pipe.  This one is built like the accumulate kernel: out-of-line products, MINB x 128 threads per SM.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) msm_reduce_tp_kernel(const uint32_t* __restrict__ S_in, const uint32_t* __restrict__ A_in,
+                                                                  uint32_t* __restrict__ S_out, uint32_t* __restrict__ A_out,
+                                                                  uint32_t m_in, uint32_t m_out, uint32_t nwin, uint32_t scale_log) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m_out * nwin) return;
+    uint32_t w = t / m_out, g = t % m_out;
+    uint64_t base = (uint64_t)w * m_in + (uint64_t)g * RED_RADIX;
+    uint32_t cnt = min((uint32_t)RED_RADIX, m_in - g * RED_RADIX);
+    G1Xyzz run, T, asum;
+    xyzz_set_inf(run); xyzz_set_inf(T); xyzz_set_inf(asum);
+#pragma unroll 1
+    for (int i = (int)cnt - 1; i >= 1; i--) {
+        {
+            G1Xyzz s = xyzz_ld(S_in, base + i);
+            xyzz_add_tp<MulCallSqr>(run, s);
+        }
+        xyzz_add_tp<MulCallSqr>(T, run);
+        if (A_in) { G1Xyzz a = xyzz_ld(A_in, base + i); xyzz_add_tp<MulCallSqr>(asum, a); }
+    }
+    {
+        G1Xyzz s = xyzz_ld(S_in, base);
+        xyzz_add_tp<MulCallSqr>(run, s);                  // run = Ssum
+        if (A_in) { G1Xyzz a = xyzz_ld(A_in, base); xyzz_add_tp<MulCallSqr>(asum, a); }
+        else asum = run;
+    }
+#pragma unroll 1
+    for (uint32_t k = 0; k < scale_log; k++) xyzz_dbl_t<MulCallSqr>(T);
+    xyzz_add_tp<MulCallSqr>(asum, T);
+    xyzz_st(S_out, (uint64_t)w * m_out + g, run);
+    xyzz_st(A_out, (uint64_t)w * m_out + g, asum);
+}
+
 // Same recurrence, one WARP per group of 32 nodes, for the upper levels of the tree where there are
 // too few groups to fill the machine and the serial 3x16 additions of a thread would be pure latency:
 // suffix sums by a 5-step scan over lanes, T and sum(A) by 5-step butterflies (15 dependent additions

@@ -127,18 +127,37 @@ def run_circuit(zk, lib, L, name, reps=3, check_all=False, threads=0):
     col_ptrs = (C.c_void_p * ncols)(*[d_ext.data_ptr() + 32 * n_ext * i for i in range(ncols)])
     MONT = zk.NTT_MONT
 
-    def resident_trace():
+    phase_names = ("h2d", "to_montgomery", "commit_columns", "lagrange_to_coeff", "zero_pad", "coeff_to_extended", "gate_program",
+                   "extended_to_coeff", "commit_quotient", "d2h")
+
+    def resident_trace(marks=None):
+        def mark():
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
+        mark()
         d_cols.copy_(sc, non_blocking=True)                                            # H2D once: ncom * n * 32 bytes
+        mark()
         zk.capi.check(lib.b200zk_fr_convert_dev(d_cols.data_ptr(), d_cols.data_ptr(), n * ncom, 1, st))
+        mark()
         zk.capi.check(lib.b200zk_msm_g1_dev(h.value, 0, d_cols.data_ptr(), n, ncom, zk.FMT_MONT, 0, d_pts.data_ptr(), st))
+        mark()
         zk.capi.check(lib.b200zk_ntt_fr_dev(d_cols.data_ptr(), ncols, k, zk.capi.addr(omega_inv), zk.NTT_INVERSE_SCALE | MONT, 0, st))
+        mark()
         zk.capi.check(lib.b200zk_fr_extend_dev(d_cols.data_ptr(), n, d_ext.data_ptr(), n_ext, ncols, st))
+        mark()
         zk.capi.check(lib.b200zk_ntt_fr_dev(d_ext.data_ptr(), ncols, ek, zk.capi.addr(omega_ext_b), zk.NTT_COSET_IN | MONT, zk.capi.addr(g), st))
+        mark()
         zk.capi.check(lib.b200zk_gate_program_run_dev(gp.handle, C.addressof(col_ptrs), d_h.data_ptr(), 0, st))
+        mark()
         zk.capi.check(lib.b200zk_ntt_fr_dev(d_h.data_ptr(), 1, ek, zk.capi.addr(omega_ext_inv),
                                             zk.NTT_INVERSE_SCALE | zk.NTT_COSET_OUT | MONT, zk.capi.addr(gi), st))
+        mark()
         zk.capi.check(lib.b200zk_msm_g1_dev(h.value, 0, d_h.data_ptr(), n, 3, zk.FMT_MONT, 0, d_pts.data_ptr() + 96 * ncom, st))
+        mark()
         h_pts.copy_(d_pts, non_blocking=True)
+        mark()
         torch.cuda.synchronize()
 
     resident_trace()
@@ -147,6 +166,9 @@ def run_circuit(zk, lib, L, name, reps=3, check_all=False, threads=0):
     for _ in range(args.reps):
         resident_trace()
     rec["gpu_resident_trace_ms"] = (time.perf_counter() - t0) / args.reps * 1e3
+    marks = []
+    resident_trace(marks)                                                              # one more pass with an event after every step
+    rec["resident_phases_ms"] = {nm: marks[i].elapsed_time(marks[i + 1]) for i, nm in enumerate(phase_names)}
     rec["resident_note"] = ("columns uploaded once and kept in HBM: %d commitments + %d inverse NTTs + %d coset NTTs of 2^%d + gate program "
                             "(%d instructions over %d columns) + quotient inverse NTT + 3 quotient commitments; D2H = %d bytes"
                             % (ncom, ncols, ncols, ek, n_instr, ncols, 96 * (ncom + 3)))
