@@ -169,3 +169,57 @@ def test_batched_guards_1024_proofs(gpu, oracle, pyref):
     assert oracle.g1_mul(left, fr(s)) != right
     params_b.release()
     params.release()
+
+
+def test_multi_open_concurrent_callers_and_changing_sizes(gpu, oracle, pyref):
+    """The opening flow keeps its scratch in per-call arenas that are reused between calls: two host threads open different
+    polynomial sets at the same time, then the sizes change (k = 9, 6, 10 -- an arena shrinks in use and grows again); every
+    proof equals the one produced alone and verifies."""
+    import threading
+    s = 0x1D0C5 * 0x7777 + 99
+    cases = {}
+    for k in (9, 6, 10):
+        params, polys, vecs, queries = setup(gpu, pyref, k, 5, 40 + k, s)
+        _, comps = commitments_of(gpu, params, polys)
+        evals = [pyref.poly_eval(polys[i], x) for i, x in queries]
+        cases[k] = (params, vecs, queries, comps, evals)
+
+    def open_one(k):
+        params, vecs, queries, comps, evals = cases[k]
+        t = gpu.host.Transcript()
+        prefix(t, comps, evals)
+        return gpu.host.multi_open(params, t, vecs, queries)
+
+    alone = {k: open_one(k) for k in (9, 6, 10)}
+    for k in (9, 6, 10):                                   # sizes in changing order, each reproducible
+        assert open_one(k) == alone[k]
+    got, errs = {}, []
+
+    def worker(k, reps):
+        try:
+            for _ in range(reps):
+                got.setdefault(k, []).append(open_one(k))
+        except Exception as e:                             # pragma: no cover - reported below
+            errs.append(e)
+
+    th = [threading.Thread(target=worker, args=(9, 6)), threading.Thread(target=worker, args=(10, 6)),
+          threading.Thread(target=worker, args=(6, 6))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for k in (9, 6, 10):
+        assert all(p == alone[k] for p in got[k]) and len(got[k]) == 6, k
+    # and the verifier accepts one of them
+    params, vecs, queries, comps, evals = cases[10]
+    t = gpu.host.Transcript()
+    prefix(t, comps, evals)
+    guard = gpu.host.multi_prepare(t, comps, [(i, x, e) for (i, x), e in zip(queries, evals)], alone[10])
+    left, right = guard.eval()
+    assert oracle.g1_mul(left, fr(s)) == right
+    guard.free()
+    for params, vecs, *_ in cases.values():
+        for v in vecs:
+            v.free()
+        params.release()

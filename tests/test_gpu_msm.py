@@ -431,3 +431,22 @@ print("chunked ok")
     env = dict(os.environ, B200ZK_MSM_CHUNK_MIN="512")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "chunked ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_table_window_bits_of_prover_size_tables(gpu, oracle):
+    """The window of a table is fixed at registration: 16 bits for 2^12 < n <= 2^18, 18 at k = 19 (measured on
+    commitment batches); whatever it is, the result is the oracle's."""
+    gpu.capi.set_profiling(True)
+    try:
+        for k, want in ((13, 16), (16, 16), (19, 18)):
+            n = 1 << k
+            bases = oracle.synth_bases(0xB200, 0, n)
+            h = register(gpu, bases, n)
+            sc = oracle.synth_scalars(60 + k, 0, n)
+            got = msm(gpu, h, sc, n)
+            prof = gpu.capi.get_profile()
+            assert prof["window_bits"] == want, (k, prof)
+            assert got == oracle.msm(bases, sc, n), k
+            gpu.capi.check(gpu.lib().b200zk_bases_release(h))
+    finally:
+        gpu.capi.set_profiling(False)

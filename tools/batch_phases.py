@@ -33,7 +33,10 @@ def main():
         zk.capi.check(lib.b200zk_bases_register_dev(d_b.data_ptr(), n, zk.FMT_MONT, 96, C.byref(h)))
         S = [circuit_bench.prover_like(np, 100 + i, n) for i in range(15)]
         U = [bench.synth_scalars_np(200 + i, 0, n) for i in range(3)]
+        only = os.environ.get("PROBE_ONLY")                   # e.g. "15S+3U": one shape (for an ncu launch list)
         for label, cols in (("15S+3U", S + U), ("15S", S), ("3U", U), ("1S", S[:1]), ("1U", U[:1]), ("5S", S[:5])):
+            if only and label != only:
+                continue
             ncol = len(cols)
             d_sc = torch.from_numpy(np.concatenate(cols).view(np.uint8).reshape(-1)).cuda()
             d_out = torch.zeros(96 * ncol, dtype=torch.uint8, device="cuda")
