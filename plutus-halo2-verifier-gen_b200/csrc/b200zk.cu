@@ -297,7 +297,7 @@ uint32_t g_tune_c = 0, g_tune_smax = 0, g_tune_variant = 6, g_tune_no_tables = 0
 bool g_profiling = false;
 Ctx* g_prof_ctx = nullptr;
 Slot* g_prof_slot = nullptr;
-int g_ntt_variant = 7;            // 7: two CTAs per SM, compile-time twiddle exponents in the lowest sweep (default); 1: without them;
+int g_ntt_variant = 9;            // 9: two CTAs per SM, compile-time twiddle exponents in the lowest sweep, uncorrected differences into the products (default); 7: with corrected differences; 1: without either;
                                   // 0: one CTA per SM; 2..6 experiments.  B200ZK_NTT_VARIANT overrides.
 int64_t g_coop8_max = 0;           // top of the bucket tree: CTA-per-group kernel while there are at most this many groups (0 = one per SM)
 int g_red_tp = 0;                  // bucket-tree levels with many groups: throughput build with this many CTAs of 128 threads per SM (0 = off)
@@ -985,6 +985,7 @@ int32_t ntt_set_attrs(Ctx& c) {
     CU(cudaFuncSetAttribute(ntt_pass_kernel_wl2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
     CU(cudaFuncSetAttribute(ntt_pass_kernel_tw2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM_TW));
     CU(cudaFuncSetAttribute(ntt_pass_kernel_lb0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
+    CU(cudaFuncSetAttribute(ntt_pass_kernel_lb0_lazy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM));
     CU(cudaFuncSetAttribute(ntt_pass_kernel_lb0_t12, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM12));
     c.ntt_attr_set = true;
     return B200ZK_OK;
@@ -1062,6 +1063,7 @@ int32_t ntt_run(Ctx& c, Slot& sl, uint32_t* d_data, uint32_t batch, uint32_t log
         else if (ntt_variant == 5) LAUNCH(ntt_pass_kernel_wl2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         else if (ntt_variant == 6) LAUNCH(ntt_pass_kernel_tw2, (unsigned)ctas, NTT_THREADS, NTT_SMEM_TW, s, a);
         else if (ntt_variant == 1) LAUNCH(ntt_pass_kernel_occ2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+        else if (ntt_variant == 9) LAUNCH(ntt_pass_kernel_lb0_lazy, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         else LAUNCH(ntt_pass_kernel_lb0, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
         TRY(prof_mark(sl, (int)i + 1, s));
         src = dst;
@@ -1555,6 +1557,7 @@ int32_t ntt_sharded(const ShardIO& io, uint32_t log_n, const uint8_t omega[32], 
                 prof_select(*c, *sl, 2);
                 TRY(prof_mark(*sl, 0, s));
                 if (g_ntt_variant == 1) LAUNCH(ntt_pass_kernel_occ2, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
+                else if (g_ntt_variant == 9) LAUNCH(ntt_pass_kernel_lb0_lazy, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
                 else LAUNCH(ntt_pass_kernel_lb0, (unsigned)ctas, NTT_THREADS, NTT_SMEM, s, a);
                 TRY(prof_mark(*sl, 1, s));
                 CU(cudaEventRecord(sl->xdev_ev, s));

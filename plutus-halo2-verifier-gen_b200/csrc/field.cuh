@@ -210,6 +210,23 @@ template <class P> HD Fe<P> fe_sub(const Fe<P>& a, const Fe<P>& b) {
     r.l[N - 1] = addc(r.l[N - 1], P::p(N - 1) & mask);
     return r;
 }
+// a - b + p in [0, 2p) for reduced a, b, without the conditional correction (two plain carry chains, no mask): for a difference
+// that goes straight into a product as the operand fe_mul walks limb by limb (its SECOND argument).  With the other operand
+// below p the running value of the interleaved reduction stays below (other + p) < 2p and the result below p (1 + 2p/R) < 2p, so
+// fe_mul's single conditional subtraction still returns the canonical residue.  Needs 2p < 2^(32 N): true for both fields.
+template <class P> HD Fe<P> fe_sub_lazy(const Fe<P>& a, const Fe<P>& b) {
+    constexpr int N = P::N;
+    Fe<P> t, r;
+    t.l[0] = sub_cc(P::p(0), b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) t.l[i] = subc_cc(P::p(i), b.l[i]);
+    t.l[N - 1] = subc(P::p(N - 1), b.l[N - 1]);
+    r.l[0] = add_cc(a.l[0], t.l[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(a.l[i], t.l[i]);
+    r.l[N - 1] = addc(a.l[N - 1], t.l[N - 1]);
+    return r;
+}
 template <class P> HD Fe<P> fe_neg(const Fe<P>& a) { return fe_sub(fe_zero<P>(), a); }
 template <class P> HD Fe<P> fe_dbl(const Fe<P>& a) { return fe_add(a, a); }
 

@@ -135,7 +135,7 @@ struct FrMulCall {
 // TWSM: the R/2 local twiddles were staged in shared memory (word planes like the data) by the caller, so a butterfly never
 // waits on a global load.  LB0: this is the sweep over index bits 0..NB-1, where the twiddle exponent of a butterfly depends
 // only on its position inside the thread (known at compile time): the multiplications by omega^0 disappear.
-template <int NB, class M, bool WL, bool TWSM = false, bool LB0 = false, int LOGB = NTT_LOGB>
+template <int NB, class M, bool WL, bool TWSM = false, bool LB0 = false, int LOGB = NTT_LOGB, bool LAZY = false>
 __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restrict__ tw_local, uint32_t deg,
                                           uint32_t lb, uint32_t tid) {
     constexpr int PLANE = (1 << LOGB) + (1 << LOGB) / 32;
@@ -171,15 +171,18 @@ __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restri
             if (j & (1 << q)) continue;
             Fr x = v[j], y = v[j | (1 << q)];
             v[j] = fe_add(x, y);
-            Fr d = fe_sub(x, y);
             if ((q == 0 && lb == 0) || (LB0 && (j & ((1 << q) - 1)) == 0)) {   // twiddle exponent is 0
-                v[j | (1 << q)] = d;
+                v[j | (1 << q)] = fe_sub(x, y);
             } else {
+                // LAZY: the difference goes straight into the product as x - y + r in [0, 2r), without the conditional
+                // correction (fe_sub_lazy: 8 LOP3 fewer per butterfly); it is the operand the product walks limb by limb,
+                // the twiddle (< r) the full-width one
+                const Fr d = LAZY ? fe_sub_lazy(x, y) : fe_sub(x, y);
                 uint32_t il = (base | ((uint32_t)j << lb)) & rmask;
                 uint32_t e = (il & ((1u << b) - 1)) << (deg - 1 - b);
                 if (LB0) e = (uint32_t)(j & ((1 << q) - 1)) << (deg - 1 - b);
                 Fr w = TWSM ? ntt_lds<false, PLANE>(sm + 8 * PLANE, e) : ntt_ldg(tw_local + 8 * (size_t)e);
-                v[j | (1 << q)] = M::mul(d, w);
+                v[j | (1 << q)] = LAZY ? M::mul(w, d) : M::mul(d, w);
             }
         }
     }
@@ -187,7 +190,7 @@ __device__ __forceinline__ void ntt_group(uint32_t* sm, const uint32_t* __restri
     for (int j = 0; j < 8; j++) ntt_sts<WL, PLANE>(sm, base | ((uint32_t)j << lb), v[j]);
 }
 
-template <class M, bool WL, bool TWSM = false, bool LB0EN = TWSM, int LOGB = NTT_LOGB>
+template <class M, bool WL, bool TWSM = false, bool LB0EN = TWSM, int LOGB = NTT_LOGB, bool LAZY = false>
 __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
     extern __shared__ uint32_t sm[];
     constexpr int PLANE = (1 << LOGB) + (1 << LOGB) / 32, THREADS = (1 << LOGB) / 8;
@@ -242,12 +245,12 @@ __device__ __forceinline__ void ntt_pass_body(const NttPassArgs& a) {
         int nb = rem >= 3 ? 3 : rem;
         uint32_t lb = (uint32_t)(rem - nb);
         if (LB0EN && lb == 0) {
-            if (nb == 3) ntt_group<3, M, WL, TWSM, true, LOGB>(sm, a.tw_local, deg, 0, tid);
-            else if (nb == 2) ntt_group<2, M, WL, TWSM, true, LOGB>(sm, a.tw_local, deg, 0, tid);
-            else ntt_group<1, M, WL, TWSM, true, LOGB>(sm, a.tw_local, deg, 0, tid);
-        } else if (nb == 3) ntt_group<3, M, WL, TWSM, false, LOGB>(sm, a.tw_local, deg, lb, tid);
-        else if (nb == 2) ntt_group<2, M, WL, TWSM, false, LOGB>(sm, a.tw_local, deg, lb, tid);
-        else ntt_group<1, M, WL, TWSM, false, LOGB>(sm, a.tw_local, deg, lb, tid);
+            if (nb == 3) ntt_group<3, M, WL, TWSM, true, LOGB, LAZY>(sm, a.tw_local, deg, 0, tid);
+            else if (nb == 2) ntt_group<2, M, WL, TWSM, true, LOGB, LAZY>(sm, a.tw_local, deg, 0, tid);
+            else ntt_group<1, M, WL, TWSM, true, LOGB, LAZY>(sm, a.tw_local, deg, 0, tid);
+        } else if (nb == 3) ntt_group<3, M, WL, TWSM, false, LOGB, LAZY>(sm, a.tw_local, deg, lb, tid);
+        else if (nb == 2) ntt_group<2, M, WL, TWSM, false, LOGB, LAZY>(sm, a.tw_local, deg, lb, tid);
+        else ntt_group<1, M, WL, TWSM, false, LOGB, LAZY>(sm, a.tw_local, deg, lb, tid);
         rem -= nb;
         // the next sweep works on bits below lb: if both this sweep and the next stay inside a warp's 256-element block
         // the warp only has to wait for itself
@@ -294,6 +297,8 @@ constexpr size_t NTT_SMEM_TW = (size_t)16 * NTT_PLANE * sizeof(uint32_t);
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_tw2(NttPassArgs a) { ntt_pass_body<FrMulInline, false, true>(a); }
 // compile-time exponents in the lowest sweep only (twiddles stay in global memory / L1)
 __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_lb0(NttPassArgs a) { ntt_pass_body<FrMulInline, false, false, true>(a); }
+// the same with uncorrected differences in the butterflies (variant 9)
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel_lb0_lazy(NttPassArgs a) { ntt_pass_body<FrMulInline, false, false, true, NTT_LOGB, true>(a); }
 // the same with a 4096-element tile (132 KiB of shared memory, 512 threads, one CTA per SM -- the same 16 warps per SM): a
 // transform of 2^23 / 2^24 points then takes two passes of radix <= 2^12 instead of three of radix 2^8
 constexpr int NTT_LOGB12 = 12;

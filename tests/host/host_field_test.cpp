@@ -61,6 +61,14 @@ template <class P> static int check_field(const char* name,
         if (!fe_eq(r, e)) { bad++; if (bad < 5) printf("%s add mismatch it=%d\n", name, it); }
         r = fe_from_mont(fe_sub(am, bm)); osub((uint8_t*)a.l, (uint8_t*)b.l, (uint8_t*)e.l);
         if (!fe_eq(r, e)) { bad++; if (bad < 5) printf("%s sub mismatch it=%d\n", name, it); }
+        {   // the NTT butterfly's product of a twiddle with an uncorrected difference: w * (x - y + p), difference in [0, 2p)
+            Fe<P> w = fe_to_mont(rnd_canon<P>()), x = am, y = bm;
+            Fe<P> pm1; for (int i = 0; i < P::N; i++) pm1.l[i] = P::p(i); pm1.l[0] -= 1;
+            if (it == 3) { x = pm1; y = fe_zero<P>(); w = pm1; }      // largest difference (2p - 1), largest twiddle
+            if (it == 4) { x = fe_zero<P>(); y = pm1; }               // smallest
+            if (it == 5) { y = x; }                                    // zero difference, represented as p
+            if (!fe_eq(fe_mul(w, fe_sub_lazy(x, y)), fe_mul(fe_sub(x, y), w))) { bad++; if (bad < 5) printf("%s sub_lazy mismatch it=%d\n", name, it); }
+        }
         if (it < 50 && !fe_is_zero(a)) {
             r = fe_from_mont(fe_inv(am)); oinv((uint8_t*)a.l, (uint8_t*)e.l);
             if (!fe_eq(r, e)) { bad++; printf("%s inv mismatch it=%d\n", name, it); }
