@@ -450,3 +450,43 @@ def test_table_window_bits_of_prover_size_tables(gpu, oracle):
             gpu.capi.check(gpu.lib().b200zk_bases_release(h))
     finally:
         gpu.capi.set_profiling(False)
+
+
+@pytest.mark.parametrize("env", [{"B200ZK_RED_TP": "3", "B200ZK_RED_TP_MIN": "1"}, {"B200ZK_RED_TP": "4", "B200ZK_RED_TP_MIN": "1"},
+                                 {"B200ZK_COOP8_MAX": "100000"}, {"B200ZK_COOP8_MAX": "1"}])
+def test_bucket_tree_kernel_choices_agree(gpu, env):
+    """The bucket tree picks its kernels by group count (serial / throughput build / warp per group / CTA per group); a child
+    process forces each choice at sizes where the default would not take it -- same commitments, with and without window
+    tables, single columns and a batch, skewed scalars included."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import ctypes as C, importlib, os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+from conftest import Oracle, _build_oracle
+zk = importlib.import_module("plutus-halo2-verifier-gen_b200")
+zk.init(-1)
+orc = Oracle(_build_oracle())
+lib, chk, addr = zk.lib(), zk.capi.check, zk.capi.addr
+R = zk.host.R_MOD
+for n, flags in ((300, 0), (5000, 0), (5000, 0x100), (70001, 0)):
+    bases = orc.synth_bases(0xB200, 9, n)
+    h = C.c_uint64(0)
+    chk(lib.b200zk_bases_register(addr(bases), n, zk.FMT_CANONICAL | flags, 96, C.byref(h)))
+    cols = [orc.synth_scalars(90 + n, 0, n), (R - 1).to_bytes(32, "little") * n,
+            b"".join((i %% 3).to_bytes(32, "little") for i in range(n))]
+    out = C.create_string_buffer(96 * len(cols))
+    chk(lib.b200zk_msm_g1_batch(h.value, 0, addr(b"".join(cols)), n, len(cols), zk.FMT_CANONICAL, addr(out)))
+    for j, sc in enumerate(cols):
+        want = orc.msm(bases, sc, n)
+        assert out.raw[96 * j:96 * j + 96] == want, (n, flags, j, "batch")
+        one = C.create_string_buffer(96)
+        chk(lib.b200zk_msm_g1(h.value, 0, addr(sc), n, zk.FMT_CANONICAL, addr(one)))
+        assert one.raw == want, (n, flags, j, "single")
+    chk(lib.b200zk_bases_release(h.value))
+print("tree ok")
+''' % (root, root)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "tree ok" in r.stdout, r.stdout + r.stderr
