@@ -354,10 +354,10 @@ int32_t eval_terms(const std::vector<Term>& terms, uint8_t out[96]) {
     std::vector<uint8_t> comp(48 * n), aff(96 * n), sc(32 * n);
     for (size_t i = 0; i < n; i++) {
         memcpy(&comp[48 * i], terms[i].pt, 48);
-        fr_store(terms[i].s, &sc[32 * i]);
+        memcpy(&sc[32 * i], terms[i].s.l, 32);       // Montgomery limbs as they are: the MSM reads them in that form
     }
     XTRY(b200zk_g1_decompress_batch(comp.data(), n, aff.data(), nullptr));
-    return b200zk_msm_g1_adhoc(aff.data(), B200ZK_FMT_CANONICAL, sc.data(), B200ZK_FMT_CANONICAL, n, out);
+    return b200zk_msm_g1_adhoc(aff.data(), B200ZK_FMT_CANONICAL, sc.data(), B200ZK_FMT_MONT, n, out);
 }
 
 // Device scratch of one multi_open: a grow-only arena per concurrent call and device, kept between calls.  cudaMalloc / cudaFree
@@ -708,6 +708,17 @@ int32_t b200zk_guard_free(uint64_t guard) {
 int32_t b200zk_guard_eval(const uint64_t* guards, uint32_t n_guards, const uint8_t* challenges, uint8_t out_left[96], uint8_t out_right[96]) {
     if (!guards || !out_left || !out_right || n_guards == 0) return ctx::fail(B200ZK_ERR_INVALID_ARG, "null pointer or no guard");
     std::vector<Term> left, right;
+    {
+        size_t nl = 0, nr = 1;
+        for (uint32_t i = 0; i < n_guards; i++) {
+            Guard* g = find_guard(guards[i]);
+            if (!g) return ctx::fail(B200ZK_ERR_BAD_HANDLE, "unknown guard handle");
+            nl += g->left.size();
+            nr += g->right.size();
+        }
+        left.reserve(nl);
+        right.reserve(nr);
+    }
     Fr gsum = fr_zero();
     for (uint32_t i = 0; i < n_guards; i++) {
         Guard* g = find_guard(guards[i]);
