@@ -190,3 +190,13 @@ def test_every_environment_switch_is_documented():
     design = open(os.path.join(ROOT, "DESIGN.md")).read()
     missing = sorted(n for n in names if n not in design)
     assert not missing, "undocumented environment switches: %s" % missing
+
+
+def test_tools_and_bench_compile():
+    """Every measurement script parses (they only run on a GPU box, where a syntax error would cost a box visit)."""
+    import ast
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))) + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    assert len(files) >= 10
+    for f in files:
+        ast.parse(open(f).read(), filename=f)
